@@ -1,0 +1,117 @@
+/* parakeet_b200 C-ABI: B200 (sm_100a) kernels for the Parakeet TTS hot path.
+ *
+ * The reference (PaddlePaddle/Parakeet) has no FFI of its own: its hot path is Python calling paddle.nn ops.
+ * This header is the boundary a Parakeet maintainer would bind instead of those ops (ctypes stub in
+ * INTEGRATION.md).  Every entry point names the reference call site (file:line under /root/reference) it replaces.
+ *
+ * Rules:
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch / C++ types;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library owns nothing but its code;
+ *   - every function returns 0 (PK_OK) or a negative error code, never throws, never aborts, never falls back to
+ *     a CPU path; pk_last_error() returns a thread-local message for the last failing call;
+ *   - all work is enqueued on the caller's stream; no internal synchronisation unless documented.
+ *
+ * Number format of GEMM operands ("split-bf16"): an fp32 tensor v is carried as two bf16 planes
+ * hi = bf16(v), lo = bf16(v - hi).  Producers in this library write both planes; pk_split_f32 converts.
+ */
+#ifndef PARAKEET_B200_H_
+#define PARAKEET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_OK 0
+#define PK_ERR_INVALID_ARG (-1)
+#define PK_ERR_CUDA (-2)
+#define PK_ERR_UNSUPPORTED (-3)
+
+#define PK_ACT_NONE 0
+#define PK_ACT_RELU 1
+#define PK_ACT_TANH 2
+
+typedef void* pk_stream_t; /* cudaStream_t */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int pk_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* pk_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches claim). */
+int64_t pk_launch_count(void);
+
+/* fp32 -> split-bf16 planes; n elements (any layout, element-wise). */
+int pk_split_f32(const float* x, void* hi, void* lo, int64_t n, pk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generic channels-last Conv1D / Linear / batched-matmul on tcgen05 tensor cores.
+ *
+ *   y[z, t, n] = act( scale * sum_{tap, k} A[za, t + (tap - pad) * dil, a_col + k] * B[zb, n, b_col + tap*Kp + k]
+ *                     + bias[n] ) + residual[z, t, n]          ; rows t >= lens[b] are written as 0
+ *
+ * with z = b * heads + h, za = b * a_bmul + h * a_hmul, a_col = a_col0 + h * a_colh (same for B), Kp = K rounded
+ * up to 64.  Rows / channels outside the declared extents read as zero (conv zero padding).
+ *
+ * Replaces, in the reference: nn.Linear call sites of MultiHeadedAttention (modules/fastspeech2_transformer/
+ * attention.py:44-47,74-78,131), the two matmuls (:153-154,126), MultiLayeredConv1d (multi_layer_conv.py:47-77),
+ * predictor Conv1D stacks (duration_predictor.py:69-83, variance_predictor.py:59-76), feat_out
+ * (models/fastspeech2/fastspeech2.py:271,457) and Postnet convs (modules/tacotron2/decoder.py:128-180).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct pk_operand {
+  const void* hi;         /* bf16 plane */
+  const void* lo;         /* bf16 plane, same layout */
+  int64_t batch_stride;   /* elements between consecutive "batches" of the plane */
+  int32_t ld;             /* elements between consecutive rows (multiple of 8) */
+  int32_t rows;           /* rows per batch; rows outside [0, rows) read as zero */
+  int32_t cols;           /* channels per row; channels outside [0, cols) read as zero */
+  int32_t batches;        /* number of batches in the plane */
+  int32_t bmul, hmul;     /* batch index used for (b, h) = b*bmul + h*hmul */
+  int32_t col0, colh;     /* first channel used for head h = col0 + h*colh */
+} pk_operand;
+
+typedef struct pk_conv_gemm_args {
+  pk_operand a;           /* activations: rows = time */
+  pk_operand b;           /* weights [n][taps*Kp] (bmul = hmul = 0) or a per-(b,h) matrix [n][K] */
+  int32_t batch, heads;   /* grid z = batch * heads */
+  int32_t m;              /* output rows per batch (time steps) */
+  int32_t n;              /* output channels */
+  int32_t k;              /* input channels per tap */
+  int32_t taps, dil, pad; /* Conv1D kernel size, dilation, left padding in taps ((taps-1)/2 for "same") */
+  float scale;            /* applied to the accumulator before bias */
+  const float* bias;      /* [n] or NULL */
+  int32_t act;            /* PK_ACT_* */
+  const float* residual;  /* fp32, indexed like y_f32, or NULL (added after act) */
+  const int32_t* lens;    /* [batch] valid rows per batch or NULL */
+  float* y_f32;           /* fp32 output or NULL */
+  void* y_hi;             /* split-bf16 output planes or NULL (both or none) */
+  void* y_lo;
+  int64_t y_batch_stride; /* elements; y offset = b*y_batch_stride + h*y_head_stride + t*y_ld + n */
+  int64_t y_head_stride;
+  int32_t y_ld;
+  int32_t passes;         /* 3 = split-bf16 (fp32-grade), 1 = plain bf16 (hi planes only) */
+} pk_conv_gemm_args;
+
+int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream);
+
+/* Same contract evaluated with plain fp32 FMAs (one thread per output element).  Debug / cross-check kernel for
+ * the tensor-core path at sizes where the CPU oracle is too slow; not used by the models. */
+int pk_conv_gemm_simt(const pk_conv_gemm_args* args, pk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Length regulator: integer repeat-expand, bit-exact row copies.
+ *   y[b, cum[b,j] + r, :] = x[b, j, :] for 0 <= r < d[b,j];  rows >= sum_j d[b,j] are 0 up to t_out.
+ * out_lens[b] = sum_j max(d[b,j],0)... (durations are clipped >= 0 upstream; negative d is rejected as in the
+ * reference's reachable domain).  Replaces LengthRegulator.expand (modules/fastspeech2_predictor/
+ * length_regulator.py:46-66): host numpy loop + 0/1-matrix matmul.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* out_lens[b] = sum_j d[b, j] (int32), device-side; t_in tokens per utterance. */
+int pk_length_regulator_lens(const int64_t* dur, int32_t batch, int32_t t_in, int32_t* out_lens, pk_stream_t stream);
+/* x: fp32 (batch, t_in, c); y: fp32 (batch, t_out, c), optional split planes y_hi / y_lo (NULL to skip). */
+int pk_length_regulate(const float* x, const int64_t* dur, int32_t batch, int32_t t_in, int32_t c, int32_t t_out,
+                       float* y, void* y_hi, void* y_lo, pk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARAKEET_B200_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libparakeet_b200.so (the C-ABI declared in include/parakeet_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libparakeet_b200.so")
+
+PK_ACT_NONE, PK_ACT_RELU, PK_ACT_TANH = 0, 1, 2
+
+
+class PkError(RuntimeError):
+    pass
+
+
+class Operand(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("batch_stride", C.c_int64), ("ld", C.c_int32),
+                ("rows", C.c_int32), ("cols", C.c_int32), ("batches", C.c_int32), ("bmul", C.c_int32),
+                ("hmul", C.c_int32), ("col0", C.c_int32), ("colh", C.c_int32)]
+
+
+class ConvGemmArgs(C.Structure):
+    _fields_ = [("a", Operand), ("b", Operand), ("batch", C.c_int32), ("heads", C.c_int32), ("m", C.c_int32),
+                ("n", C.c_int32), ("k", C.c_int32), ("taps", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
+                ("scale", C.c_float), ("bias", C.c_void_p), ("act", C.c_int32), ("residual", C.c_void_p),
+                ("lens", C.c_void_p), ("y_f32", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p),
+                ("y_batch_stride", C.c_int64), ("y_head_stride", C.c_int64), ("y_ld", C.c_int32),
+                ("passes", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises PkError when the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PkError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.pk_version.restype = C.c_int
+        L.pk_last_error.restype = C.c_char_p
+        L.pk_launch_count.restype = C.c_int64
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def _declare(L):
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sigs = {
+        "pk_split_f32": [vp, vp, vp, i64, vp],
+        "pk_conv_gemm": [C.POINTER(ConvGemmArgs), vp],
+        "pk_conv_gemm_simt": [C.POINTER(ConvGemmArgs), vp],
+        "pk_length_regulator_lens": [vp, i32, i32, vp, vp],
+        "pk_length_regulate": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    del f32
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pk_last_error().decode("utf-8", "replace")
+        raise PkError(f"{what} failed with code {rc}: {msg}")
+
+
+def launch_count():
+    return int(lib().pk_launch_count())
+
+
+def exported_symbols():
+    """Names declared in include/parakeet_b200.h (used by the CPU-side symbol test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "parakeet_b200.h")
+    text = open(hdr).read()
+    return sorted(set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(pk_\w+)\s*\(", text, flags=re.M)))

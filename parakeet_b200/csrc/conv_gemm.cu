@@ -1,0 +1,367 @@
+// pk_conv_gemm: channels-last Conv1D / Linear / batched matmul as an im2col-free tiled GEMM on tcgen05.
+//
+//   - one CTA per 128(time) x BLOCK_N(channel) output tile, 192 threads:
+//       warp 0   : TMA producer  (one elected lane)
+//       warp 1   : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//       warps 2-5: epilogue (TMEM -> registers -> bias/act/residual/mask -> global), one output row per thread
+//   - K loop over (tap, 64-channel chunk): each conv tap is just the same A tensor read `(tap - pad) * dil` rows
+//     further along; TMA zero-fills rows outside the utterance, which is the conv's zero padding (no im2col).
+//   - split-bf16 operands, 3 MMAs per K-step (hi*hi + lo*hi + hi*lo), fp32 accumulation in TMEM.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "pk_host.h"
+#include "pk_sm100.cuh"
+
+namespace pk {
+
+constexpr int kBlockM = 128;
+constexpr int kGemmThreads = 192;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kSwizzleBytes;       // one plane of one A chunk (16 KB)
+  static constexpr int kBBytes = BLOCK_N * kSwizzleBytes;       // one plane of one B chunk
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // hi + lo
+  static constexpr int kStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+struct GemmKernelArgs {
+  int m, n, k_chunks, taps, dil, pad, heads;
+  int a_bmul, a_hmul, a_col0, a_colh;
+  int b_bmul, b_hmul, b_col0, b_colh, b_tap_stride;
+  float scale;
+  const float* bias;
+  int act;
+  const float* residual;
+  const int32_t* lens;
+  float* y_f32;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  long long y_batch_stride, y_head_stride;
+  int y_ld;
+  int passes;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const GemmKernelArgs p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int bz = blockIdx.z / p.heads;
+  const int hz = blockIdx.z % p.heads;
+  const int num_chunks = p.taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      const int a_batch = bz * p.a_bmul + hz * p.a_hmul;
+      const int b_batch = bz * p.b_bmul + hz * p.b_hmul;
+      const int a_col = p.a_col0 + hz * p.a_colh;
+      const int b_col = p.b_col0 + hz * p.b_colh;
+      const uint32_t tx_bytes = (p.passes == 3) ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes);
+      for (int i = 0; i < num_chunks; ++i) {
+        const int s = i % Cfg::kStages;
+        const uint32_t ph = (i / Cfg::kStages) & 1;
+        const int tap = i / p.k_chunks;
+        const int kc = i % p.k_chunks;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        const int a_row = m0 + (tap - p.pad) * p.dil;
+        tma_load_3d(st, &tm_a_hi, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
+        tma_load_3d(st + 2 * Cfg::kABytes, &tm_b_hi, &full_bar[s], b_col + tap * p.b_tap_stride + kc * kChunkK, n0, b_batch);
+        if (p.passes == 3) {
+          tma_load_3d(st + Cfg::kABytes, &tm_a_lo, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
+          tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s],
+                      b_col + tap * p.b_tap_stride + kc * kChunkK, n0, b_batch);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
+      for (int i = 0; i < num_chunks; ++i) {
+        const int s = i % Cfg::kStages;
+        const uint32_t ph = (i / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint64_t a_hi = make_smem_desc_sw128(st);
+        const uint64_t a_lo = make_smem_desc_sw128(st + Cfg::kABytes);
+        const uint64_t b_hi = make_smem_desc_sw128(st + 2 * Cfg::kABytes);
+        const uint64_t b_lo = make_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // 32 B per K-step inside the 128B row
+          umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, (i | k) != 0);
+          if (p.passes == 3) {
+            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
+            umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;   // output time step
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const bool row_ok = row < p.m;
+    const bool row_live = row_ok && (p.lens == nullptr || row < p.lens[bz]);
+    const long long y_off = bz * p.y_batch_stride + hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      float v[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (row_ok && nb < p.n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = nb + j;
+          float x = v[j] * p.scale;
+          if (p.bias != nullptr && n < p.n) x += __ldg(p.bias + n);
+          if (p.act == PK_ACT_RELU) x = fmaxf(x, 0.f);
+          else if (p.act == PK_ACT_TANH) x = tanhf(x);
+          v[j] = x;
+        }
+        const bool full = (nb + 32 <= p.n) && ((p.y_ld & 7) == 0) && (((y_off + nb) & 7) == 0);
+        if (p.residual != nullptr) {
+          if (full) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + y_off + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = __ldg(r4 + j);
+              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.n) v[j] += __ldg(p.residual + y_off + nb + j);
+          }
+        }
+        if (!row_live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (full) {
+          if (p.y_f32 != nullptr) {
+            float4* o4 = reinterpret_cast<float4*>(p.y_f32 + y_off + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.y_hi != nullptr) {
+            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + y_off + nb);
+            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + y_off + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 h, l;
+              split8(v + 8 * j, h, l);
+              oh[j] = h;
+              ol[j] = l;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < p.n) {
+              if (p.y_f32 != nullptr) p.y_f32[y_off + nb + j] = v[j];
+              if (p.y_hi != nullptr) {
+                __nv_bfloat16 h, l;
+                split_bf16(v[j], h, l);
+                p.y_hi[y_off + nb + j] = h;
+                p.y_lo[y_off + nb + j] = l;
+              }
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// fp32 SIMT evaluation of the same contract (debug / cross-check).
+__global__ void conv_gemm_simt_kernel(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, const __nv_bfloat16* b_hi,
+                                      const __nv_bfloat16* b_lo, pk_operand oa, pk_operand ob, GemmKernelArgs p, int k,
+                                      int batch) {
+  const long long total = static_cast<long long>(batch) * p.heads * p.m * p.n;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = idx % p.n;
+    const int t = (idx / p.n) % p.m;
+    const int z = idx / (static_cast<long long>(p.n) * p.m);
+    const int b = z / p.heads, h = z % p.heads;
+    const long long ab = (b * p.a_bmul + h * p.a_hmul) * oa.batch_stride;
+    const long long bb = (b * p.b_bmul + h * p.b_hmul) * ob.batch_stride;
+    const int ac = p.a_col0 + h * p.a_colh, bc = p.b_col0 + h * p.b_colh;
+    float acc = 0.f;
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const int r = t + (tap - p.pad) * p.dil;
+      if (r < 0 || r >= oa.rows) continue;
+      for (int kk = 0; kk < k; ++kk) {
+        if (ac + kk >= oa.cols) break;
+        const long long ai = ab + static_cast<long long>(r) * oa.ld + ac + kk;
+        const int bcol = bc + tap * p.b_tap_stride + kk;
+        if (bcol >= ob.cols || n >= ob.rows) continue;
+        const long long bi = bb + static_cast<long long>(n) * ob.ld + bcol;
+        float av = __bfloat162float(a_hi[ai]);
+        float bv = __bfloat162float(b_hi[bi]);
+        if (p.passes == 3) {
+          av += __bfloat162float(a_lo[ai]);
+          bv += __bfloat162float(b_lo[bi]);
+        }
+        acc = fmaf(av, bv, acc);
+      }
+    }
+    float x = acc * p.scale;
+    if (p.bias) x += p.bias[n];
+    if (p.act == PK_ACT_RELU) x = fmaxf(x, 0.f);
+    else if (p.act == PK_ACT_TANH) x = tanhf(x);
+    const long long yo = b * p.y_batch_stride + h * p.y_head_stride + static_cast<long long>(t) * p.y_ld + n;
+    if (p.residual) x += p.residual[yo];
+    if (p.lens && t >= p.lens[b]) x = 0.f;
+    if (p.y_f32) p.y_f32[yo] = x;
+    if (p.y_hi) {
+      __nv_bfloat16 hh, ll;
+      split_bf16(x, hh, ll);
+      p.y_hi[yo] = hh;
+      p.y_lo[yo] = ll;
+    }
+  }
+}
+
+static int validate(const pk_conv_gemm_args* a) {
+  PK_CHECK_ARG(a != nullptr, "args is NULL");
+  PK_CHECK_ARG(a->a.hi && a->b.hi, "operand hi planes must be non-NULL");
+  PK_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3 (got %d)", a->passes);
+  PK_CHECK_ARG(a->passes == 1 || (a->a.lo && a->b.lo), "passes=3 needs lo planes");
+  PK_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->m > 0 && a->n > 0 && a->k > 0, "batch/heads/m/n/k must be > 0");
+  PK_CHECK_ARG(a->taps >= 1 && a->dil >= 1 && a->pad >= 0, "bad taps/dil/pad");
+  PK_CHECK_ARG((a->a.ld % 8) == 0 && (a->b.ld % 8) == 0, "operand row strides must be multiples of 8 elements (16 B)");
+  PK_CHECK_ARG((a->a.batch_stride % 8) == 0 && (a->b.batch_stride % 8) == 0, "operand batch strides must be multiples of 8");
+  PK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a.hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b.hi) & 15) == 0,
+               "operand planes must be 16-byte aligned");
+  PK_CHECK_ARG((a->y_f32 != nullptr) || (a->y_hi != nullptr), "no output requested");
+  PK_CHECK_ARG((a->y_hi == nullptr) == (a->y_lo == nullptr), "y_hi and y_lo must both be set or both NULL");
+  PK_CHECK_ARG(a->act >= PK_ACT_NONE && a->act <= PK_ACT_TANH, "unknown activation %d", a->act);
+  PK_CHECK_ARG(static_cast<long long>(a->batch) * a->heads <= 65535, "batch*heads exceeds grid.z limit");
+  return PK_OK;
+}
+
+static GemmKernelArgs to_kernel_args(const pk_conv_gemm_args* a) {
+  GemmKernelArgs p;
+  p.m = a->m; p.n = a->n; p.k_chunks = (a->k + kChunkK - 1) / kChunkK; p.taps = a->taps; p.dil = a->dil; p.pad = a->pad;
+  p.heads = a->heads;
+  p.a_bmul = a->a.bmul; p.a_hmul = a->a.hmul; p.a_col0 = a->a.col0; p.a_colh = a->a.colh;
+  p.b_bmul = a->b.bmul; p.b_hmul = a->b.hmul; p.b_col0 = a->b.col0; p.b_colh = a->b.colh;
+  p.b_tap_stride = p.k_chunks * kChunkK;
+  p.scale = a->scale; p.bias = a->bias; p.act = a->act; p.residual = a->residual; p.lens = a->lens;
+  p.y_f32 = a->y_f32; p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  p.y_batch_stride = a->y_batch_stride; p.y_head_stride = a->y_head_stride; p.y_ld = a->y_ld;
+  p.passes = a->passes;
+  return p;
+}
+
+template <int BLOCK_N>
+static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = encode_tmap_bf16_3d(&ta_hi, a->a.hi, a->a.cols, a->a.rows, a->a.batches, a->a.ld, a->a.batch_stride, kBlockM))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tb_hi, a->b.hi, a->b.cols, a->b.rows, a->b.batches, a->b.ld, a->b.batch_stride, BLOCK_N))) return rc;
+  if (a->passes == 3) {
+    if ((rc = encode_tmap_bf16_3d(&ta_lo, a->a.lo, a->a.cols, a->a.rows, a->a.batches, a->a.ld, a->a.batch_stride, kBlockM))) return rc;
+    if ((rc = encode_tmap_bf16_3d(&tb_lo, a->b.lo, a->b.cols, a->b.rows, a->b.batches, a->b.ld, a->b.batch_stride, BLOCK_N))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const GemmKernelArgs p = to_kernel_args(a);
+  dim3 grid((a->m + kBlockM - 1) / kBlockM, (a->n + BLOCK_N - 1) / BLOCK_N, a->batch * a->heads);
+  conv_gemm_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
+}  // namespace pk
+
+extern "C" int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream) {
+  int rc = pk::validate(args);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // tile width with the fewest padded columns (ties -> wider tile)
+  const int n = args->n;
+  auto waste = [n](int bn) { return (n + bn - 1) / bn * bn - n; };
+  if (n <= 64) return pk::launch<64>(args, s);
+  if (waste(256) <= waste(128) && n > 128) return pk::launch<256>(args, s);
+  return pk::launch<128>(args, s);
+}
+
+extern "C" int pk_conv_gemm_simt(const pk_conv_gemm_args* args, pk_stream_t stream) {
+  int rc = pk::validate(args);
+  if (rc) return rc;
+  const pk::GemmKernelArgs p = pk::to_kernel_args(args);
+  const long long total = static_cast<long long>(args->batch) * args->heads * args->m * args->n;
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, 148LL * 16));
+  pk::conv_gemm_simt_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(args->a.hi), static_cast<const __nv_bfloat16*>(args->a.lo),
+      static_cast<const __nv_bfloat16*>(args->b.hi), static_cast<const __nv_bfloat16*>(args->b.lo), args->a, args->b, p,
+      args->k, args->batch);
+  PK_CHECK_CUDA(cudaGetLastError());
+  pk::count_launch();
+  return PK_OK;
+}

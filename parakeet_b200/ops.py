@@ -1,0 +1,166 @@
+"""Torch-tensor level wrappers over the C-ABI (device memory + streams are torch's; all math is in the .so)."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import PK_ACT_NONE, PK_ACT_RELU, PK_ACT_TANH, ConvGemmArgs, Operand  # noqa: F401
+
+ACTS = {None: PK_ACT_NONE, "none": PK_ACT_NONE, "relu": PK_ACT_RELU, "tanh": PK_ACT_TANH}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.PkError("parakeet_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+class Split:
+    """split-bf16 tensor: value = hi + lo (two bf16 planes of identical shape / strides)."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        assert hi.dtype == torch.bfloat16 and lo.dtype == torch.bfloat16 and hi.shape == lo.shape
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @staticmethod
+    def empty(shape, device):
+        return Split(torch.empty(shape, dtype=torch.bfloat16, device=device),
+                     torch.empty(shape, dtype=torch.bfloat16, device=device))
+
+    @staticmethod
+    def zeros(shape, device):
+        return Split(torch.zeros(shape, dtype=torch.bfloat16, device=device),
+                     torch.zeros(shape, dtype=torch.bfloat16, device=device))
+
+    @staticmethod
+    def from_f32(x):
+        """fp32 CUDA tensor -> split planes (pk_split_f32)."""
+        _require_cuda(x)
+        x = x.contiguous().float()
+        out = Split.empty(x.shape, x.device)
+        _lib.check(_lib.lib().pk_split_f32(_ptr(x), _ptr(out.hi), _ptr(out.lo), x.numel(), _stream()), "pk_split_f32")
+        return out
+
+    def float(self):
+        return self.hi.float() + self.lo.float()
+
+
+def pack_weight(w, device=None):
+    """Conv1D weight [out, in, k] (Paddle/torch layout) or Linear weight given as [out, in] ->
+    K-major GEMM operand [out, k * Kp] (tap-major, each tap's channels zero-padded to a multiple of 64), split-bf16.
+    Host-side, done once at load time."""
+    w = w.detach().float().cpu()
+    if w.dim() == 2:
+        w = w.unsqueeze(-1)
+    n, k, taps = w.shape
+    kp = (k + 63) // 64 * 64
+    packed = torch.zeros(n, taps, kp, dtype=torch.float32)
+    packed[:, :, :k] = w.permute(0, 2, 1)
+    packed = packed.reshape(n, taps * kp)
+    hi = packed.to(torch.bfloat16)
+    lo = (packed - hi.float()).to(torch.bfloat16)
+    dev = device or "cuda"
+    return Split(hi.to(dev).contiguous(), lo.to(dev).contiguous())
+
+
+def _operand(s, rows, cols, ld, batch_stride, batches, bmul=1, hmul=0, col0=0, colh=0):
+    return Operand(hi=s.hi.data_ptr(), lo=s.lo.data_ptr(), batch_stride=batch_stride, ld=ld, rows=rows, cols=cols,
+                   batches=batches, bmul=bmul, hmul=hmul, col0=col0, colh=colh)
+
+
+def conv_gemm(a, w, *, n, k, taps=1, dil=1, pad=None, bias=None, act=None, residual=None, lens=None, scale=1.0,
+              out_f32=True, out_split=False, passes=3, simt=False, y_f32=None, y_split=None):
+    """Channels-last Conv1D / Linear.  a: Split (B, T, C_total); w: packed weight Split [n, taps*Kp].
+
+    Returns (y_f32 or None, y_split or None), each (B, T, n).
+    """
+    _require_cuda(a.hi, w.hi)
+    B, T, Ctot = a.hi.shape
+    if pad is None:
+        pad = (taps - 1) // 2
+    dev = a.hi.device
+    if out_f32 and y_f32 is None:
+        y_f32 = torch.empty(B, T, n, dtype=torch.float32, device=dev)
+    if out_split and y_split is None:
+        y_split = Split.empty((B, T, n), dev)
+    args = ConvGemmArgs()
+    args.a = _operand(a, rows=T, cols=Ctot, ld=a.hi.stride(1), batch_stride=a.hi.stride(0), batches=B)
+    args.b = _operand(w, rows=w.hi.shape[0], cols=w.hi.shape[1], ld=w.hi.stride(0), batch_stride=0, batches=1, bmul=0)
+    args.batch, args.heads, args.m, args.n, args.k = B, 1, T, n, k
+    args.taps, args.dil, args.pad = taps, dil, pad
+    args.scale = scale
+    args.bias = bias.data_ptr() if bias is not None else None
+    args.act = ACTS[act]
+    args.residual = residual.data_ptr() if residual is not None else None
+    args.lens = lens.data_ptr() if lens is not None else None
+    args.y_f32 = y_f32.data_ptr() if y_f32 is not None else None
+    args.y_hi = y_split.hi.data_ptr() if y_split is not None else None
+    args.y_lo = y_split.lo.data_ptr() if y_split is not None else None
+    args.y_batch_stride, args.y_head_stride, args.y_ld = T * n, 0, n
+    args.passes = passes
+    fn = _lib.lib().pk_conv_gemm_simt if simt else _lib.lib().pk_conv_gemm
+    _lib.check(fn(C.byref(args), _stream()), "pk_conv_gemm")
+    return y_f32, y_split
+
+
+def batched_matmul_nt(a, b, *, batch, heads, m, n, k, a_spec, b_spec, scale=1.0, y_f32=None, y_split=None,
+                      y_batch_stride=None, y_head_stride=None, y_ld=None, lens=None, passes=3, simt=False):
+    """y[b,h] = scale * A[b,h] (m x k) . B[b,h]^T (n x k); operand addressing given by a_spec / b_spec dicts
+    (rows, cols, ld, batch_stride, batches, bmul, hmul, col0, colh)."""
+    args = ConvGemmArgs()
+    args.a = _operand(a, **a_spec)
+    args.b = _operand(b, **b_spec)
+    args.batch, args.heads, args.m, args.n, args.k = batch, heads, m, n, k
+    args.taps, args.dil, args.pad = 1, 1, 0
+    args.scale = scale
+    args.act = PK_ACT_NONE
+    args.lens = lens.data_ptr() if lens is not None else None
+    args.y_f32 = y_f32.data_ptr() if y_f32 is not None else None
+    args.y_hi = y_split.hi.data_ptr() if y_split is not None else None
+    args.y_lo = y_split.lo.data_ptr() if y_split is not None else None
+    args.y_batch_stride, args.y_head_stride, args.y_ld = y_batch_stride, y_head_stride, y_ld
+    args.passes = passes
+    fn = _lib.lib().pk_conv_gemm_simt if simt else _lib.lib().pk_conv_gemm
+    _lib.check(fn(C.byref(args), _stream()), "pk_conv_gemm")
+
+
+def length_regulator_lens(dur):
+    """dur: int64 (B, T) CUDA -> int32 (B,) total frames per utterance (device tensor, no sync)."""
+    _require_cuda(dur)
+    dur = dur.contiguous()
+    B, T = dur.shape
+    out = torch.empty(B, dtype=torch.int32, device=dur.device)
+    _lib.check(_lib.lib().pk_length_regulator_lens(_ptr(dur), B, T, _ptr(out), _stream()), "pk_length_regulator_lens")
+    return out
+
+
+def length_regulate(x, dur, t_out, want_f32=True, want_split=False):
+    """x fp32 (B, T, C), dur int64 (B, T) -> (B, t_out, C) repeat-expanded; rows past sum(d) are zero."""
+    _require_cuda(x, dur)
+    x = x.contiguous()
+    dur = dur.contiguous()
+    B, T, Cc = x.shape
+    y = torch.empty(B, t_out, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
+    ys = Split.empty((B, t_out, Cc), x.device) if want_split else None
+    _lib.check(_lib.lib().pk_length_regulate(_ptr(x), _ptr(dur), B, T, Cc, t_out, _ptr(y),
+                                             _ptr(ys.hi) if ys else None, _ptr(ys.lo) if ys else None, _stream()),
+               "pk_length_regulate")
+    return y, ys
+
+
+__all__ = ["Split", "pack_weight", "conv_gemm", "batched_matmul_nt", "length_regulate", "length_regulator_lens", "math"]
