@@ -111,6 +111,58 @@ int pk_length_regulator_lens(const int64_t* dur, int32_t batch, int32_t t_in, in
 int pk_length_regulate(const float* x, const int64_t* dur, int32_t batch, int32_t t_in, int32_t c, int32_t t_out,
                        float* y, void* y_hi, void* y_lo, pk_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Parallel WaveGAN generator (reference: parakeet/models/parallel_wavegan/parallel_wavegan.py).
+ * Activations are channels-last split-bf16 planes (B, T, C); conditioning c is (B, T, aux).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ConvInUpsampleNet.forward (:201-216) = conv_in (Conv1D aux->aux, k = 2*window+1, no padding, no bias) followed by
+ * UpsampleNet.forward (:119-138): per scale s, nearest stretch x s (Stretch2D :48-63) then a (1, 2s+1) FIR with zero
+ * padding s.  mel: device fp32 (batch, aux, frames + 2*window), channel-first like the reference;
+ * conv_in_w: device fp32 [aux][aux][2*window+1]; fir: HOST fp32, the n_stages FIRs concatenated (2*s_k+1 taps each);
+ * scales: HOST int32 [n_stages].  Outputs (either may be NULL): c_f32 (batch, aux, T) channel-first fp32 and
+ * c_hi/c_lo (batch, T, aux) channels-last split-bf16, T = frames * prod(scales). */
+int pk_pwg_upsample(const float* mel, const float* conv_in_w, const float* fir, const int32_t* scales, int32_t n_stages,
+                    int32_t batch, int32_t aux, int32_t frames, int32_t window, float* c_f32, void* c_hi, void* c_lo,
+                    pk_stream_t stream);
+
+/* first_conv (:401-402, :464): x[b,t,r] = w[r] * noise[b,t] + bias[r] for 64 residual channels, written as split
+ * planes (batch, t, 64); rows t >= lens[b] are written as zero (lens may be NULL). */
+int pk_pwg_first_conv(const float* noise, const float* w, const float* bias, const int32_t* lens, int32_t batch, int32_t t,
+                      void* x_hi, void* x_lo, pk_stream_t stream);
+
+/* One fused ResidualBlock.forward (:284-315) for residual = skip = 64 channels, gate = 128, kernel 3:
+ *   h = conv_k3_dil(x) + b1 + conv1x1_aux(c);  z = tanh(h[:64]) * sigmoid(h[64:]);
+ *   skip (+)= conv1x1_skip(z) + b_skip;  y = (conv1x1_out(z) + b_out + x) * sqrt(0.5)
+ * w1: packed [128][5*64] K-major = taps 0..2 (64 ch each) then the aux weight zero-padded to 128 channels;
+ * w2: packed [128][64], rows 0..63 = conv1x1_skip, rows 64..127 = conv1x1_out; bias1 [128]; bias2 = skip bias | out bias.
+ * y must not alias x.  Rows t >= lens[b] of y are written as zero and tiles wholly past lens[b] are skipped
+ * (their y rows must already be zero). */
+typedef struct pk_pwg_layer_args {
+  int32_t batch, t, dilation, aux_channels;
+  const int32_t* lens;     /* [batch] valid samples or NULL */
+  const void* x_hi;        /* input planes (batch, t, 64) */
+  const void* x_lo;
+  void* y_hi;              /* output planes (batch, t, 64) */
+  void* y_lo;
+  const void* c_hi;        /* conditioning planes (batch, t, aux_channels) */
+  const void* c_lo;
+  const void* w1_hi;
+  const void* w1_lo;
+  const void* w2_hi;
+  const void* w2_lo;
+  const float* bias1;
+  const float* bias2;
+  float* skip;             /* fp32 (batch, t, 64) running sum of skips */
+  int32_t skip_init;       /* 1: overwrite (first layer), 0: accumulate */
+} pk_pwg_layer_args;
+int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
+
+/* last_conv_layers (:429-440) on the scaled skip sum (:469-471): out[row] = w2 . relu(W1 relu(skip[row] * scale) + b1) + b2
+ * with skip fp32 (rows, 64), W1 [64 out][64 in], w2 [64]; out fp32 (rows). */
+int pk_pwg_tail(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float scale,
+                int64_t rows, float* out, pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

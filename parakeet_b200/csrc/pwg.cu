@@ -1,0 +1,584 @@
+// Parallel WaveGAN generator kernels (reference: parakeet/models/parallel_wavegan/parallel_wavegan.py).
+//
+//   pk_pwg_residual_layer : one fused ResidualBlock (:284-315) over the whole batch, channels-last, tcgen05:
+//        GEMM1  h[128 t x 128]  = sum_{tap} x[t + (tap-1) d, 0:64] W_conv[tap] + c[t, 0:80] W_aux      (K = 272)
+//        gate   z[128 x 64]     = tanh(h[:, :64] + b) * sigmoid(h[:, 64:] + b)       (TMEM -> regs -> smem, never HBM)
+//        GEMM2  [skip | out]    = z W_so                                              (K = 64)
+//        epi    skip_acc += skip + b_skip ;  x_out = (out + b_out + x) * sqrt(0.5)
+//     persistent CTAs (one per SM), 10 warps: TMA producer, MMA issuer, 8 epilogue warps; double-buffered TMEM
+//     accumulators so GEMM1 of tile i+1 overlaps the gate/epilogue of tile i.
+//   pk_pwg_upsample       : ConvInUpsampleNet (:201-216) conv_in + [nearest stretch + FIR] x scales, fused per frame.
+//   pk_pwg_first_conv     : first_conv 1 -> R channels (:464).
+//   pk_pwg_tail           : skips * sqrt(1/L) -> ReLU -> 1x1 -> ReLU -> 1x1 (:469-471).
+#include <algorithm>
+
+#include "pk_host.h"
+#include "pk_sm100.cuh"
+
+namespace pk {
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused residual layer
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPwgR = 64;        // residual channels
+constexpr int kPwgG = 128;       // gate channels
+constexpr int kPwgS = 64;        // skip channels
+constexpr int kPwgStages = 3;
+constexpr int kPwgTile = 128 * kSwizzleBytes;                 // 16 KB: one plane of a 128-row K-chunk
+constexpr int kPwgStageBytes = 4 * kPwgTile;                  // A hi, A lo, B hi, B lo
+constexpr int kPwgZBytes = 2 * kPwgTile;                      // z hi, z lo
+constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgZBytes + 1024 + 256;
+constexpr int kPwgEpiWarps = 8;
+constexpr int kPwgThreads = 64 + kPwgEpiWarps * 32;           // 320
+constexpr int kPwgG1Chunks = 5;                               // 3 taps + 2 aux chunks (64 + 16 channels)
+
+struct PwgLayerArgs {
+  int batch, t, dil, aux_ch;
+  int tiles_per_b, total_tiles;
+  const int32_t* lens;          // valid samples per utterance or NULL
+  const float* bias1;           // [128] conv bias
+  const float* bias2;           // [128] skip bias | out bias
+  float* skip;                  // fp32 (B, T, 64) accumulator
+  int skip_init;                // 1: write, 0: accumulate
+  const __nv_bfloat16* x_hi;    // layer input planes (B, T, 64) (re-read for the residual add)
+  const __nv_bfloat16* x_lo;
+  __nv_bfloat16* y_hi;          // layer output planes
+  __nv_bfloat16* y_lo;
+};
+
+struct PwgTileIter {
+  int idx, step, tiles_per_b, total, t;
+  const int32_t* lens;
+  __device__ PwgTileIter(const PwgLayerArgs& p) : idx(static_cast<int>(blockIdx.x) - static_cast<int>(gridDim.x)),
+      step(gridDim.x), tiles_per_b(p.tiles_per_b), total(p.total_tiles), t(p.t), lens(p.lens) {}
+  // advance to the next tile that holds at least one valid sample
+  __device__ bool next(int& b, int& m0) {
+    for (;;) {
+      idx += step;
+      if (idx >= total) return false;
+      b = idx / tiles_per_b;
+      m0 = (idx % tiles_per_b) * 128;
+      const int len = lens ? min(__ldg(lens + b), t) : t;
+      if (m0 < len) return true;
+    }
+  }
+};
+
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return __fdividef(2.f, 1.f + __expf(-2.f * v)) - 1.f; }
+
+__global__ void __launch_bounds__(kPwgThreads, 1)
+pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                 const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
+                 const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                 const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                 const PwgLayerArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* z_smem = smem + kPwgStages * kPwgStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(z_smem + kPwgZBytes);
+  uint64_t* full_bar = bars;                       // [stages]
+  uint64_t* empty_bar = full_bar + kPwgStages;     // [stages]
+  uint64_t* acc1_full = empty_bar + kPwgStages;    // [2]
+  uint64_t* acc1_empty = acc1_full + 2;            // [2]
+  uint64_t* acc2_full = acc1_empty + 2;            // [2]
+  uint64_t* acc2_empty = acc2_full + 2;            // [2]
+  uint64_t* z_full = acc2_empty + 2;               // [1]
+  uint64_t* z_empty = z_full + 1;                  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_c_hi); tma_prefetch_desc(&tm_c_lo);
+    tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w1_lo); tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo);
+    for (int s = 0; s < kPwgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kPwgEpiWarps * 32);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kPwgEpiWarps * 32);
+    }
+    mbar_init(z_full, kPwgEpiWarps * 32);
+    mbar_init(z_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      uint32_t it = 0;  // running stage counter
+      auto load_g1 = [&](int b, int m0) {
+        for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
+          const int s = it % kPwgStages;
+          mbar_wait(&empty_bar[s], ((it / kPwgStages) & 1) ^ 1);
+          uint8_t* st = smem + s * kPwgStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], kPwgStageBytes);
+          if (j < 3) {
+            const int row = m0 + (j - 1) * p.dil;
+            tma_load_3d(st, &tm_x_hi, &full_bar[s], 0, row, b);
+            tma_load_3d(st + kPwgTile, &tm_x_lo, &full_bar[s], 0, row, b);
+          } else {
+            tma_load_3d(st, &tm_c_hi, &full_bar[s], (j - 3) * kChunkK, m0, b);
+            tma_load_3d(st + kPwgTile, &tm_c_lo, &full_bar[s], (j - 3) * kChunkK, m0, b);
+          }
+          tma_load_3d(st + 2 * kPwgTile, &tm_w1_hi, &full_bar[s], j * kChunkK, 0, 0);
+          tma_load_3d(st + 3 * kPwgTile, &tm_w1_lo, &full_bar[s], j * kChunkK, 0, 0);
+        }
+      };
+      auto load_g2 = [&]() {
+        const int s = it % kPwgStages;
+        mbar_wait(&empty_bar[s], ((it / kPwgStages) & 1) ^ 1);
+        uint8_t* st = smem + s * kPwgStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * kPwgTile);
+        tma_load_3d(st + 2 * kPwgTile, &tm_w2_hi, &full_bar[s], 0, 0, 0);
+        tma_load_3d(st + 3 * kPwgTile, &tm_w2_lo, &full_bar[s], 0, 0, 0);
+        ++it;
+      };
+      PwgTileIter ti(p);
+      int b, m0, nb, nm0;
+      bool have = ti.next(b, m0);
+      if (have) load_g1(b, m0);
+      while (have) {
+        const bool have_next = ti.next(nb, nm0);
+        if (have_next) load_g1(nb, nm0);
+        load_g2();
+        have = have_next; b = nb; m0 = nm0;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128, 128);
+      const int aux_tail_ksteps = ((p.aux_ch - kChunkK) + kUmmaK - 1) / kUmmaK;  // k-steps in the 2nd aux chunk
+      uint32_t it = 0;
+      auto mma_chunk = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int ksteps, bool first) {
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+          umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, !(first && k == 0));
+          umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+          umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+        }
+      };
+      auto g1 = [&](int i) {
+        const int buf = i & 1;
+        mbar_wait(&acc1_empty[buf], ((i >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + buf * 128;
+        for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
+          const int s = it % kPwgStages;
+          mbar_wait(&full_bar[s], (it / kPwgStages) & 1);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + s * kPwgStageBytes);
+          mma_chunk(d, make_smem_desc_sw128(st), make_smem_desc_sw128(st + kPwgTile), make_smem_desc_sw128(st + 2 * kPwgTile),
+                    make_smem_desc_sw128(st + 3 * kPwgTile), j == kPwgG1Chunks - 1 ? aux_tail_ksteps : 4, j == 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc1_full[buf]);
+      };
+      auto g2 = [&](int i) {
+        const int buf = i & 1;
+        mbar_wait(z_full, i & 1);
+        mbar_wait(&acc2_empty[buf], ((i >> 1) & 1) ^ 1);
+        const int s = it % kPwgStages;
+        mbar_wait(&full_bar[s], (it / kPwgStages) & 1);
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + s * kPwgStageBytes);
+        const uint32_t zs = smem_u32(z_smem);
+        mma_chunk(tmem_base + 256 + buf * 128, make_smem_desc_sw128(zs), make_smem_desc_sw128(zs + kPwgTile),
+                  make_smem_desc_sw128(st + 2 * kPwgTile), make_smem_desc_sw128(st + 3 * kPwgTile), 4, true);
+        umma_commit(&empty_bar[s]);
+        umma_commit(z_empty);
+        umma_commit(&acc2_full[buf]);
+        ++it;
+      };
+      PwgTileIter ti(p);
+      int b, m0;
+      int n_issued = 0;   // tiles whose GEMM1 has been issued
+      int n_done = 0;     // tiles whose GEMM2 has been issued
+      bool have = ti.next(b, m0);
+      if (have) g1(n_issued++);
+      while (have) {
+        const bool have_next = ti.next(b, m0);
+        if (have_next) g1(n_issued++);
+        g2(n_done++);
+        have = have_next;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;     // TMEM lane quarter accessible to this warp
+    const int half = ew >> 2;         // which half of the columns this warp handles
+    const int r = quarter * 32 + lane;  // row inside the tile
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const float kSqrtHalf = 0.70710678118654752440f;
+    PwgTileIter ti(p);
+    int b, m0;
+    for (int i = 0; ti.next(b, m0); ++i) {
+      const int buf = i & 1;
+      const int t = m0 + r;
+      const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
+      // ---- E1: gate ----
+      mbar_wait(&acc1_full[buf], (i >> 1) & 1);
+      tcgen05_fence_after();
+      float va[32], vb[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_base + lane_base + buf * 128 + half * 32, va);
+      tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&acc1_empty[buf]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = va[j] + __ldg(p.bias1 + half * 32 + j);
+        const float g = vb[j] + __ldg(p.bias1 + 64 + half * 32 + j);
+        va[j] = fast_tanh(a) * fast_sigmoid(g);
+      }
+      mbar_wait(z_empty, (i & 1) ^ 1);  // GEMM2 of the previous tile has finished reading z
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 h, l;
+        split8(va + 8 * q, h, l);
+        const int chunk = (half * 4 + q) ^ (r & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+        *reinterpret_cast<uint4*>(z_smem + r * kSwizzleBytes + chunk * 16) = h;
+        *reinterpret_cast<uint4*>(z_smem + kPwgTile + r * kSwizzleBytes + chunk * 16) = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(z_full);
+      // ---- E2: skip / residual ----
+      mbar_wait(&acc2_full[buf], (i >> 1) & 1);
+      tcgen05_fence_after();
+      float v0[32], v1[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64, v0);
+      tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64 + 32, v1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&acc2_empty[buf]);
+      if (t < p.t) {
+        const long long row_off = (static_cast<long long>(b) * p.t + t) * 64;
+        if (half == 0) {
+          // skip accumulation (fp32)
+          float4* sp = reinterpret_cast<float4*>(p.skip + row_off);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float* v = q < 8 ? v0 + 4 * q : v1 + 4 * (q - 8);
+            float4 acc = make_float4(v[0] + __ldg(p.bias2 + 4 * q), v[1] + __ldg(p.bias2 + 4 * q + 1),
+                                     v[2] + __ldg(p.bias2 + 4 * q + 2), v[3] + __ldg(p.bias2 + 4 * q + 3));
+            if (!p.skip_init) {
+              const float4 o = sp[q];
+              acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            sp[q] = acc;
+          }
+        } else {
+          // residual: x_out = (out + b_out + x_in) * sqrt(0.5); rows past the utterance end stay zero
+          const uint4* xh = reinterpret_cast<const uint4*>(p.x_hi + row_off);
+          const uint4* xl = reinterpret_cast<const uint4*>(p.x_lo + row_off);
+          uint4* yh = reinterpret_cast<uint4*>(p.y_hi + row_off);
+          uint4* yl = reinterpret_cast<uint4*>(p.y_lo + row_off);
+          const bool live = t < len;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float* v = q < 4 ? v0 + 8 * q : v1 + 8 * (q - 4);
+            const uint4 h4 = __ldg(xh + q), l4 = __ldg(xl + q);
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+            const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = bf16_bits_to_float(hw[e] & 0xffffu) + bf16_bits_to_float(lw[e] & 0xffffu);
+              const float x1 = bf16_bits_to_float(hw[e] >> 16) + bf16_bits_to_float(lw[e] >> 16);
+              o[2 * e] = live ? (v[2 * e] + __ldg(p.bias2 + 64 + 8 * q + 2 * e) + x0) * kSqrtHalf : 0.f;
+              o[2 * e + 1] = live ? (v[2 * e + 1] + __ldg(p.bias2 + 64 + 8 * q + 2 * e + 1) + x1) * kSqrtHalf : 0.f;
+            }
+            uint4 oh, ol;
+            split8(o, oh, ol);
+            yh[q] = oh;
+            yl[q] = ol;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ConvInUpsampleNet: conv_in (no padding) then up to 4 x [nearest stretch by s, FIR of 2s+1 taps, zero padded]
+// grid = (frames, batch); one CTA produces the hop = prod(scales) output samples of one frame for all channels.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kUpMaxStages = 4;
+constexpr int kUpMaxTaps = 33;
+struct UpsampleArgs {
+  int n_stages;
+  int scale[kUpMaxStages];
+  float fir[kUpMaxStages][kUpMaxTaps];
+  int aux, frames, window;       // channels, T' (after conv_in), aux_context_window
+  int hop;
+};
+
+__global__ void __launch_bounds__(256)
+pwg_upsample_kernel(const float* __restrict__ mel,        // (B, aux, frames + 2*window) channel-first, like the reference
+                    const float* __restrict__ w_in,       // conv_in weight [aux][aux][2*window+1]
+                    const UpsampleArgs a, float* __restrict__ c_f32 /* (B, aux, T) or NULL */,
+                    __nv_bfloat16* __restrict__ c_hi, __nv_bfloat16* __restrict__ c_lo /* (B, T, aux) or NULL */) {
+  extern __shared__ float up_smem[];
+  const int j = blockIdx.x, b = blockIdx.y;
+  const int aux = a.aux;
+  // Per-stage ranges needed to produce outputs [lo_out, hi_out) of the last stage, walked backwards.
+  // stage k output index range [lo[k], hi[k]) (may stick out of the valid range; such values are zero).
+  int lo[kUpMaxStages + 1], hi[kUpMaxStages + 1], len[kUpMaxStages + 1];
+  len[0] = a.frames;
+  for (int k = 0; k < a.n_stages; ++k) len[k + 1] = len[k] * a.scale[k];
+  lo[a.n_stages] = j * a.hop;
+  hi[a.n_stages] = (j + 1) * a.hop;
+  for (int k = a.n_stages - 1; k >= 0; --k) {
+    const int s = a.scale[k];
+    // y[t] = sum_q w[q] * u[t + q - s], u[i] = in[floor(i / s)] for 0 <= i < s*len[k] else 0
+    int l = lo[k + 1] - s, h = hi[k + 1] - 1 + s;   // u index range (inclusive h)
+    l = l < 0 ? -((-l + s - 1) / s) : l / s;
+    h = h < 0 ? -((-h + s - 1) / s) : h / s;
+    lo[k] = l;
+    hi[k] = h + 1;
+  }
+  // smem layout: stage k buffer [aux][hi[k]-lo[k]]
+  float* buf[kUpMaxStages + 1];
+  int width[kUpMaxStages + 1];
+  {
+    float* ptr = up_smem;
+    for (int k = 0; k <= a.n_stages; ++k) {
+      width[k] = hi[k] - lo[k];
+      buf[k] = ptr;                       // the last stage is written straight to global memory
+      if (k < a.n_stages) ptr += aux * width[k];
+    }
+  }
+  const int kin = 2 * a.window + 1;
+  const int mel_len = a.frames + 2 * a.window;
+  // stage 0: conv_in outputs m[ch][f] for f in [lo[0], hi[0]) (zero outside [0, frames))
+  for (int idx = threadIdx.x; idx < aux * width[0]; idx += blockDim.x) {
+    const int ch = idx / width[0], f = lo[0] + idx % width[0];
+    float acc = 0.f;
+    if (f >= 0 && f < a.frames) {
+      const float* mp = mel + (static_cast<long long>(b) * aux) * mel_len + f;
+      const float* wp = w_in + static_cast<long long>(ch) * aux * kin;
+      for (int ci = 0; ci < aux; ++ci)
+        for (int q = 0; q < kin; ++q) acc = fmaf(__ldg(wp + ci * kin + q), __ldg(mp + static_cast<long long>(ci) * mel_len + q), acc);
+    }
+    buf[0][idx] = acc;
+  }
+  __syncthreads();
+  for (int k = 0; k < a.n_stages; ++k) {
+    const int s = a.scale[k], taps = 2 * s + 1;
+    const int ulen = s * len[k];
+    const bool last = (k == a.n_stages - 1);
+    for (int idx = threadIdx.x; idx < aux * width[k + 1]; idx += blockDim.x) {
+      // for the last stage iterate channel-fastest so the channels-last global store is coalesced
+      const int ch = last ? idx % aux : idx / width[k + 1];
+      const int tt = last ? idx / aux : idx % width[k + 1];
+      const int t = lo[k + 1] + tt;
+      float acc = 0.f;
+      if (t >= 0 && t < len[k + 1]) {
+        for (int q = 0; q < taps; ++q) {
+          const int ui = t + q - s;
+          if (ui >= 0 && ui < ulen) acc = fmaf(a.fir[k][q], buf[k][ch * width[k] + (ui / s - lo[k])], acc);
+        }
+      }
+      if (!last) {
+        buf[k + 1][ch * width[k + 1] + tt] = acc;
+      } else {
+        const long long T = len[k + 1];
+        if (c_f32) c_f32[(static_cast<long long>(b) * aux + ch) * T + t] = acc;
+        if (c_hi) {
+          __nv_bfloat16 h, l;
+          split_bf16(acc, h, l);
+          c_hi[(static_cast<long long>(b) * T + t) * aux + ch] = h;
+          c_lo[(static_cast<long long>(b) * T + t) * aux + ch] = l;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// first_conv: x[b, t, r] = w[r] * noise[b, t] + bias[r]  (in_channels = 1), written as split planes, masked by lens
+__global__ void pwg_first_conv_kernel(const float* __restrict__ noise, const float* __restrict__ w, const float* __restrict__ bias,
+                                      const int32_t* __restrict__ lens, int t_len, long long total_rows,
+                                      __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo) {
+  // one thread per (row, 8-channel group): 8 groups per row
+  const long long n = total_rows * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = idx >> 3;
+    const int g = idx & 7;
+    const int b = row / t_len, t = row % t_len;
+    const bool live = lens == nullptr || t < __ldg(lens + b);
+    const float xv = __ldg(noise + row);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = live ? fmaf(__ldg(w + g * 8 + e), xv, __ldg(bias + g * 8 + e)) : 0.f;
+    uint4 h, l;
+    split8(v, h, l);
+    reinterpret_cast<uint4*>(x_hi)[idx] = h;
+    reinterpret_cast<uint4*>(x_lo)[idx] = l;
+  }
+}
+
+// tail: y = W2 relu(W1 relu(skips * scale) + b1) + b2, skip channels = 64, out channels = 1
+__global__ void __launch_bounds__(256)
+pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ w1 /*[64][64] out,in*/, const float* __restrict__ b1,
+                const float* __restrict__ w2 /*[64]*/, const float* __restrict__ b2, float scale, long long rows,
+                float* __restrict__ out) {
+  __shared__ float sw1[64 * 65];
+  __shared__ float sb1[64], sw2[64];
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) sw1[(i / 64) * 65 + (i % 64)] = w1[i];
+  if (threadIdx.x < 64) { sb1[threadIdx.x] = b1[threadIdx.x]; sw2[threadIdx.x] = w2[threadIdx.x]; }
+  __syncthreads();
+  const float bias2 = __ldg(b2);
+  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < rows;
+       row += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s[64];
+    const float4* sp = reinterpret_cast<const float4*>(skip + row * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 v = __ldg(sp + q);
+      s[4 * q] = fmaxf(v.x * scale, 0.f); s[4 * q + 1] = fmaxf(v.y * scale, 0.f);
+      s[4 * q + 2] = fmaxf(v.z * scale, 0.f); s[4 * q + 3] = fmaxf(v.w * scale, 0.f);
+    }
+    float y = bias2;
+    for (int o = 0; o < 64; ++o) {
+      float acc = sb1[o];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) acc = fmaf(sw1[o * 65 + k], s[k], acc);
+      y = fmaf(sw2[o], fmaxf(acc, 0.f), y);
+    }
+    out[row] = y;
+  }
+}
+
+}  // namespace pk
+
+// ===============================================================================================================
+// C-ABI
+// ===============================================================================================================
+extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t stream) {
+  PK_CHECK_ARG(a != nullptr, "args is NULL");
+  PK_CHECK_ARG(a->batch > 0 && a->t > 0 && a->dilation >= 1, "bad batch/t/dilation");
+  PK_CHECK_ARG(a->aux_channels > 64 && a->aux_channels <= 128 && (a->aux_channels % 8) == 0,
+               "aux_channels must be in (64,128] and a multiple of 8 (got %d)", a->aux_channels);
+  PK_CHECK_ARG(a->x_hi && a->x_lo && a->y_hi && a->y_lo && a->c_hi && a->c_lo && a->w1_hi && a->w1_lo && a->w2_hi && a->w2_lo &&
+               a->bias1 && a->bias2 && a->skip, "NULL pointer in pk_pwg_layer_args");
+  PK_CHECK_ARG(a->x_hi != a->y_hi, "layer output must not alias its input (neighbouring tiles read the input halo)");
+  using namespace pk;
+  CUtensorMap tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
+  int rc;
+  const uint64_t T = a->t, B = a->batch;
+  if ((rc = encode_tmap_bf16_3d(&tx_hi, a->x_hi, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tx_lo, a->x_lo, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tc_hi, a->c_hi, a->aux_channels, T, B, a->aux_channels, T * a->aux_channels, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tc_lo, a->c_lo, a->aux_channels, T, B, a->aux_channels, T * a->aux_channels, 128))) return rc;
+  const uint64_t k1 = kPwgG1Chunks * kChunkK;  // 320: 3 taps x 64 + aux padded to 128
+  if ((rc = encode_tmap_bf16_3d(&tw1_hi, a->w1_hi, k1, kPwgG, 1, k1, 0, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw1_lo, a->w1_lo, k1, kPwgG, 1, k1, 0, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw2_hi, a->w2_hi, 64, 128, 1, 64, 0, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw2_lo, a->w2_lo, 64, 128, 1, 64, 0, 128))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwgSmem));
+    attr_set = true;
+  }
+  PwgLayerArgs p;
+  p.batch = a->batch; p.t = a->t; p.dil = a->dilation; p.aux_ch = a->aux_channels;
+  p.tiles_per_b = (a->t + 127) / 128;
+  p.total_tiles = p.tiles_per_b * a->batch;
+  p.lens = a->lens; p.bias1 = a->bias1; p.bias2 = a->bias2; p.skip = a->skip; p.skip_init = a->skip_init;
+  p.x_hi = static_cast<const __nv_bfloat16*>(a->x_hi); p.x_lo = static_cast<const __nv_bfloat16*>(a->x_lo);
+  p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  const int grid = std::min(p.total_tiles, sm_count());
+  pwg_layer_kernel<<<grid, kPwgThreads, kPwgSmem, static_cast<cudaStream_t>(stream)>>>(tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi, tw1_lo,
+                                                                                        tw2_hi, tw2_lo, p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
+extern "C" int pk_pwg_upsample(const float* mel, const float* conv_in_w, const float* fir, const int32_t* scales,
+                               int32_t n_stages, int32_t batch, int32_t aux, int32_t frames, int32_t window, float* c_f32,
+                               void* c_hi, void* c_lo, pk_stream_t stream) {
+  using namespace pk;
+  PK_CHECK_ARG(mel && conv_in_w && fir && scales, "NULL pointer");
+  PK_CHECK_ARG(n_stages >= 1 && n_stages <= kUpMaxStages, "n_stages must be in [1,%d]", kUpMaxStages);
+  PK_CHECK_ARG(batch > 0 && aux > 0 && frames > 0 && window >= 0, "bad sizes");
+  PK_CHECK_ARG(c_f32 || c_hi, "no output requested");
+  PK_CHECK_ARG((c_hi == nullptr) == (c_lo == nullptr), "c_hi and c_lo must both be set or both NULL");
+  UpsampleArgs a;
+  a.n_stages = n_stages; a.aux = aux; a.frames = frames; a.window = window; a.hop = 1;
+  for (int k = 0; k < n_stages; ++k) {
+    PK_CHECK_ARG(scales[k] >= 1 && 2 * scales[k] + 1 <= kUpMaxTaps, "upsample scale %d unsupported", scales[k]);
+    a.scale[k] = scales[k];
+    a.hop *= scales[k];
+    for (int q = 0; q < 2 * scales[k] + 1; ++q) a.fir[k][q] = *fir++;  // host pointer (tiny FIRs, concatenated)
+  }
+  // smem: sum over stages of aux * width; widths bounded by hop_k + 2 (+halo)
+  size_t floats = 0;
+  {
+    int lo = 0, hi = a.hop;
+    int w[kUpMaxStages + 1];
+    w[n_stages] = hi - lo;
+    for (int k = n_stages - 1; k >= 0; --k) {
+      const int s = a.scale[k];
+      w[k] = (w[k + 1] + 2 * s) / s + 2;
+    }
+    for (int k = 0; k < n_stages; ++k) floats += static_cast<size_t>(aux) * (w[k] + 2);
+  }
+  const size_t smem = floats * sizeof(float);
+  PK_CHECK_ARG(smem <= 200 * 1024, "upsample tile does not fit shared memory (%zu bytes)", smem);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_upsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  dim3 grid(frames, batch);
+  pwg_upsample_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(mel, conv_in_w, a, c_f32,
+                                                                              static_cast<__nv_bfloat16*>(c_hi),
+                                                                              static_cast<__nv_bfloat16*>(c_lo));
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
+extern "C" int pk_pwg_first_conv(const float* noise, const float* w, const float* bias, const int32_t* lens, int32_t batch,
+                                 int32_t t, void* x_hi, void* x_lo, pk_stream_t stream) {
+  PK_CHECK_ARG(noise && w && bias && x_hi && x_lo, "NULL pointer");
+  PK_CHECK_ARG(batch > 0 && t > 0, "bad sizes");
+  const long long rows = static_cast<long long>(batch) * t;
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<long long>((rows * 8 + threads - 1) / threads, pk::sm_count() * 16LL));
+  pk::pwg_first_conv_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      noise, w, bias, lens, t, rows, static_cast<__nv_bfloat16*>(x_hi), static_cast<__nv_bfloat16*>(x_lo));
+  PK_CHECK_CUDA(cudaGetLastError());
+  pk::count_launch();
+  return PK_OK;
+}
+
+extern "C" int pk_pwg_tail(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float scale,
+                           int64_t rows, float* out, pk_stream_t stream) {
+  PK_CHECK_ARG(skip && w1 && b1 && w2 && b2 && out, "NULL pointer");
+  PK_CHECK_ARG(rows > 0, "bad sizes");
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<long long>((rows + threads - 1) / threads, pk::sm_count() * 8LL));
+  pk::pwg_tail_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(skip, w1, b1, w2, b2, scale, rows, out);
+  PK_CHECK_CUDA(cudaGetLastError());
+  pk::count_launch();
+  return PK_OK;
+}

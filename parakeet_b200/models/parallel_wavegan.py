@@ -1,0 +1,301 @@
+"""Parallel WaveGAN generator on B200 - host side.
+
+Mirrors parakeet/models/parallel_wavegan/parallel_wavegan.py of the reference: `PWGGenerator` (:318-520) with the same
+constructor keywords, `forward(x, c)`, `inference(c)`, `apply_weight_norm` / `remove_weight_norm`, and the same
+state-dict key names (`first_conv.*`, `upsample_net.conv_in.weight`, `upsample_net.upsample.up_layers.{1,3,5,7}.weight`,
+`conv_layers.{i}.{conv,conv1x1_aux,conv1x1_out,conv1x1_skip}.*`, `last_conv_layers.{1,3}.*`; `weight_g` [out] /
+`weight_v` while weight norm is applied); `PWGInference` (:766-775).
+
+All arithmetic runs in libparakeet_b200.so (pk_pwg_* in include/parakeet_b200.h); torch only owns the buffers.
+"""
+import ctypes as C
+import math
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..layer import Layer
+from ..ops import Split, _ptr, _stream
+
+_lib_sigs_done = False
+
+
+def _declare():
+    global _lib_sigs_done
+    if _lib_sigs_done:
+        return
+    L = _lib.lib()
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.pk_pwg_upsample.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.pk_pwg_first_conv.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.pk_pwg_residual_layer.argtypes = [C.POINTER(PwgLayerArgs), vp]
+    L.pk_pwg_tail.argtypes = [vp, vp, vp, vp, vp, f32, i64, vp, vp]
+    for n in ("pk_pwg_upsample", "pk_pwg_first_conv", "pk_pwg_residual_layer", "pk_pwg_tail"):
+        getattr(L, n).restype = C.c_int
+    _lib_sigs_done = True
+
+
+class PwgLayerArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("dilation", C.c_int32), ("aux_channels", C.c_int32),
+                ("lens", C.c_void_p), ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p),
+                ("y_lo", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("w1_hi", C.c_void_p),
+                ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p), ("bias1", C.c_void_p),
+                ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32)]
+
+
+def _split_host(w, device):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return Split(hi.to(device).contiguous(), lo.to(device).contiguous())
+
+
+class PWGGenerator(Layer):
+    """Wave generator of Parallel WaveGAN (reference parallel_wavegan.py:318-443 for the constructor)."""
+
+    def __init__(self,
+                 in_channels: int = 1,
+                 out_channels: int = 1,
+                 kernel_size: int = 3,
+                 layers: int = 30,
+                 stacks: int = 3,
+                 residual_channels: int = 64,
+                 gate_channels: int = 128,
+                 skip_channels: int = 64,
+                 aux_channels: int = 80,
+                 aux_context_window: int = 2,
+                 dropout: float = 0.,
+                 bias: bool = True,
+                 use_weight_norm: bool = True,
+                 use_causal_conv: bool = False,
+                 upsample_scales: List[int] = [4, 4, 4, 4],
+                 nonlinear_activation: Optional[str] = None,
+                 nonlinear_activation_params: Dict[str, Any] = {},
+                 interpolate_mode: str = "nearest",
+                 freq_axis_kernel_size: int = 1,
+                 device=None,
+                 seed: int = 0):
+        super().__init__(device)
+        if use_causal_conv:
+            raise NotImplementedError("use_causal_conv=True is out of scope (the reference's causal branch indexes "
+                                      "instead of slicing, parallel_wavegan.py:305)")
+        if nonlinear_activation is not None:
+            raise NotImplementedError("upsample-net activations are not used by the shipped configs")
+        if interpolate_mode != "nearest" or freq_axis_kernel_size != 1:
+            raise NotImplementedError("only nearest interpolation / freq_axis_kernel_size=1 are supported")
+        if (in_channels, out_channels, kernel_size, residual_channels, gate_channels, skip_channels) != (1, 1, 3, 64, 128, 64):
+            raise NotImplementedError("the sm_100a kernels are specialised for 1/1 io channels, kernel 3, 64/128/64 channels")
+        if not (64 < aux_channels <= 128 and aux_channels % 8 == 0):
+            raise NotImplementedError("aux_channels must be in (64, 128] and a multiple of 8")
+        if dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is a training-time feature (next round)")
+        assert layers % stacks == 0
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.aux_channels, self.aux_context_window = aux_channels, aux_context_window
+        self.layers, self.stacks, self.kernel_size = layers, stacks, kernel_size
+        self.upsample_scales = list(upsample_scales)
+        self.upsample_factor = int(np.prod(upsample_scales))
+        self.use_bias = bias
+        self._weight_norm = False
+        self._ws = {}
+
+        g = torch.Generator().manual_seed(seed)
+
+        def conv(name, o, i, *k, with_bias=True):
+            bound = 1.0 / math.sqrt(i * math.prod(k))
+            self._register(name + ".weight", (torch.rand(o, i, *k, generator=g) * 2 - 1) * bound)
+            if with_bias:
+                self._register(name + ".bias", (torch.rand(o, generator=g) * 2 - 1) * bound)
+
+        R, G, S, A = residual_channels, gate_channels, skip_channels, aux_channels
+        conv("first_conv", R, in_channels, 1)
+        conv("upsample_net.conv_in", A, A, 2 * aux_context_window + 1, with_bias=False)
+        for i, s in enumerate(self.upsample_scales):
+            conv(f"upsample_net.upsample.up_layers.{2 * i + 1}", 1, 1, 1, 2 * s + 1, with_bias=False)
+        for i in range(layers):
+            pre = f"conv_layers.{i}."
+            conv(pre + "conv", G, R, kernel_size, with_bias=bias)
+            conv(pre + "conv1x1_aux", G, A, 1, with_bias=False)
+            conv(pre + "conv1x1_out", R, G // 2, 1, with_bias=bias)
+            conv(pre + "conv1x1_skip", S, G // 2, 1, with_bias=bias)
+        conv("last_conv_layers.1", S, S, 1)
+        conv("last_conv_layers.3", out_channels, S, 1)
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    # -- weight norm (reference :474-496) ---------------------------------------------------------------------
+    def apply_weight_norm(self):
+        """weight -> (weight_g [out], weight_v) with g = ||v|| (paddle.nn.utils.weight_norm, dim=0)."""
+        if self._weight_norm:
+            return
+        new = type(self._params)()
+        for k, v in self._params.items():
+            if k.endswith(".weight"):
+                new[k + "_g"] = v.reshape(v.shape[0], -1).norm(dim=1)
+                new[k + "_v"] = v
+            else:
+                new[k] = v
+        self._params = new
+        self._weight_norm = True
+        self._packed = None
+
+    def remove_weight_norm(self):
+        if not self._weight_norm:
+            return
+        self._params = type(self._params)(self._folded().items())
+        self._weight_norm = False
+        self._packed = None
+
+    def _folded(self):
+        """state with weight_g / weight_v folded into weight = g * v / ||v|| (done once per weight change)."""
+        if not self._weight_norm:
+            return self._params
+        out = type(self._params)()
+        for k, v in self._params.items():
+            if k.endswith("weight_g"):
+                continue
+            if k.endswith("weight_v"):
+                g = self._params[k[:-1] + "g"]
+                norm = v.reshape(v.shape[0], -1).norm(dim=1)
+                out[k[:-2]] = v * (g / norm).reshape([-1] + [1] * (v.dim() - 1))
+            else:
+                out[k] = v
+        return out
+
+    # -- kernel-ready weights ------------------------------------------------------------------------------------
+    def _pack(self):
+        if self._packed is not None:
+            return self._packed
+        p = {k: v.detach().float().cpu() for k, v in self._folded().items()}
+        dev = self.device
+        pk = {}
+        pk["conv_in_w"] = p["upsample_net.conv_in.weight"].contiguous().to(dev)
+        fir = [p[f"upsample_net.upsample.up_layers.{2 * i + 1}.weight"].reshape(-1) for i in range(len(self.upsample_scales))]
+        pk["fir_host"] = np.ascontiguousarray(torch.cat(fir).numpy(), dtype=np.float32)
+        pk["scales_host"] = np.asarray(self.upsample_scales, dtype=np.int32)
+        pk["first_w"] = p["first_conv.weight"].reshape(-1).contiguous().to(dev)
+        pk["first_b"] = p["first_conv.bias"].contiguous().to(dev)
+        A = self.aux_channels
+        layers = []
+        zeros64 = torch.zeros(64)
+        for i in range(self.layers):
+            pre = f"conv_layers.{i}."
+            w = p[pre + "conv.weight"]                       # [128, 64, 3]
+            w1 = torch.zeros(128, 5 * 64)
+            for tap in range(3):
+                w1[:, tap * 64:(tap + 1) * 64] = w[:, :, tap]
+            w1[:, 192:192 + A] = p[pre + "conv1x1_aux.weight"][:, :, 0]
+            w2 = torch.cat([p[pre + "conv1x1_skip.weight"][:, :, 0], p[pre + "conv1x1_out.weight"][:, :, 0]], dim=0)  # [128, 64]
+            b1 = p.get(pre + "conv.bias", torch.zeros(128))
+            b2 = torch.cat([p.get(pre + "conv1x1_skip.bias", zeros64), p.get(pre + "conv1x1_out.bias", zeros64)])
+            layers.append(dict(w1=_split_host(w1, dev), w2=_split_host(w2, dev), b1=b1.contiguous().to(dev),
+                               b2=b2.contiguous().to(dev), dil=2 ** (i % (self.layers // self.stacks))))
+        pk["layers"] = layers
+        pk["tail_w1"] = p["last_conv_layers.1.weight"][:, :, 0].contiguous().to(dev)
+        pk["tail_b1"] = p["last_conv_layers.1.bias"].contiguous().to(dev)
+        pk["tail_w2"] = p["last_conv_layers.3.weight"].reshape(-1).contiguous().to(dev)
+        pk["tail_b2"] = p["last_conv_layers.3.bias"].contiguous().to(dev)
+        self._packed = pk
+        return pk
+
+    def _workspace(self, B, T):
+        key = (B, T)
+        ws = self._ws.get(key)
+        if ws is None:
+            self._ws.clear()
+            dev = self.device
+            ws = dict(xa=Split.zeros((B, T, 64), dev), xb=Split.zeros((B, T, 64), dev),
+                      c=Split.empty((B, T, self.aux_channels), dev),
+                      skip=torch.empty(B, T, 64, dtype=torch.float32, device=dev))
+            self._ws[key] = ws
+        return ws
+
+    # -- forward (reference :445-472) ------------------------------------------------------------------------------
+    def forward(self, x, c, lens=None):
+        """x: (B, 1, T) noise, c: (B, aux, T' + 2*aux_context_window) -> (B, 1, T).
+
+        `lens` (optional, int32 (B,) valid samples per utterance) lets a ragged batch run as one call: every
+        utterance is then generated exactly as if it were alone (zero padding at its own end)."""
+        _declare()
+        L = _lib.lib()
+        if not (x.is_cuda and c.is_cuda):
+            raise _lib.PkError("PWGGenerator.forward needs CUDA tensors (no CPU fallback)")
+        pk = self._pack()
+        B, _, T = x.shape
+        frames = c.shape[-1] - 2 * self.aux_context_window
+        assert frames * self.upsample_factor == T, (c.shape, x.shape)   # reference :462
+        ws = self._workspace(B, T)
+        st = _stream()
+        x = x.contiguous().float()
+        c = c.contiguous().float()
+        lens_p = _ptr(lens) if lens is not None else None
+        if lens is not None:
+            assert lens.dtype == torch.int32 and lens.is_cuda
+        _lib.check(L.pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]), pk["fir_host"].ctypes.data_as(C.c_void_p),
+                                     pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
+                                     self.aux_channels, frames, self.aux_context_window, None, _ptr(ws["c"].hi),
+                                     _ptr(ws["c"].lo), st), "pk_pwg_upsample")
+        _lib.check(L.pk_pwg_first_conv(_ptr(x), _ptr(pk["first_w"]), _ptr(pk["first_b"]), lens_p, B, T, _ptr(ws["xa"].hi),
+                                       _ptr(ws["xa"].lo), st), "pk_pwg_first_conv")
+        if lens is not None:
+            ws["xb"].hi.zero_()
+            ws["xb"].lo.zero_()
+        src, dst = ws["xa"], ws["xb"]
+        args = PwgLayerArgs()
+        args.batch, args.t, args.aux_channels = B, T, self.aux_channels
+        args.lens = lens.data_ptr() if lens is not None else None
+        args.c_hi, args.c_lo = ws["c"].hi.data_ptr(), ws["c"].lo.data_ptr()
+        args.skip = ws["skip"].data_ptr()
+        for i, lay in enumerate(pk["layers"]):
+            args.dilation = lay["dil"]
+            args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
+            args.w1_hi, args.w1_lo = lay["w1"].hi.data_ptr(), lay["w1"].lo.data_ptr()
+            args.w2_hi, args.w2_lo = lay["w2"].hi.data_ptr(), lay["w2"].lo.data_ptr()
+            args.bias1, args.bias2 = lay["b1"].data_ptr(), lay["b2"].data_ptr()
+            args.skip_init = 1 if i == 0 else 0
+            _lib.check(L.pk_pwg_residual_layer(C.byref(args), st), "pk_pwg_residual_layer")
+            src, dst = dst, src
+        out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
+        _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
+                                 _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
+        self._last_x = src  # layer-30 residual stream (tests)
+        return out
+
+    def upsample(self, c):
+        """ConvInUpsampleNet.forward (:201-216) alone: (B, aux, T'+2w) -> (B, aux, T) fp32 (used by the tests)."""
+        _declare()
+        pk = self._pack()
+        B = c.shape[0]
+        frames = c.shape[-1] - 2 * self.aux_context_window
+        out = torch.empty(B, self.aux_channels, frames * self.upsample_factor, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().pk_pwg_upsample(_ptr(c.contiguous().float()), _ptr(pk["conv_in_w"]),
+                                              pk["fir_host"].ctypes.data_as(C.c_void_p),
+                                              pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
+                                              self.aux_channels, frames, self.aux_context_window, _ptr(out), None, None,
+                                              _stream()), "pk_pwg_upsample")
+        return out
+
+    def inference(self, c=None, x=None):
+        """Single-utterance generation (reference :498-520): c (T', aux) -> (T, out_channels).
+        The noise is drawn with torch.randn unless `x` (1, 1, T) is supplied (parity tests supply it)."""
+        T = c.shape[0] * self.upsample_factor
+        if x is None:
+            x = torch.randn(1, self.in_channels, T, device=self.device)
+        c = c.transpose(0, 1).unsqueeze(0)
+        w = self.aux_context_window
+        c = torch.cat([c[:, :, :1].expand(-1, -1, w), c, c[:, :, -1:].expand(-1, -1, w)], dim=-1)  # Pad1D 'replicate'
+        return self.forward(x, c).squeeze(0).transpose(0, 1)
+
+
+class PWGInference(Layer):
+    """reference parallel_wavegan.py:766-775."""
+
+    def __init__(self, normalizer, pwg_generator):
+        super().__init__(pwg_generator.device)
+        self.normalizer = normalizer
+        self.pwg_generator = pwg_generator
+
+    def forward(self, logmel, x=None):
+        normalized_mel = self.normalizer(logmel)
+        return self.pwg_generator.inference(normalized_mel, x=x)
