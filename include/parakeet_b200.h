@@ -121,10 +121,12 @@ int pk_length_regulate(const float* x, const int64_t* dur, int32_t batch, int32_
  * padding s.  mel: device fp32 (batch, aux, frames + 2*window), channel-first like the reference;
  * conv_in_w: device fp32 [aux][aux][2*window+1]; fir: HOST fp32, the n_stages FIRs concatenated (2*s_k+1 taps each);
  * scales: HOST int32 [n_stages].  Outputs (either may be NULL): c_f32 (batch, aux, T) channel-first fp32 and
- * c_hi/c_lo (batch, T, aux) channels-last split-bf16, T = frames * prod(scales). */
+ * c_hi/c_lo (batch, T, aux) channels-last split-bf16, T = frames * prod(scales).  frame_lens (device int32 [batch] or
+ * NULL): valid frames per utterance of a ragged batch; each utterance is then upsampled exactly as if alone
+ * (zero padding at its own end) and its samples past frame_lens[b]*hop are written as zero. */
 int pk_pwg_upsample(const float* mel, const float* conv_in_w, const float* fir, const int32_t* scales, int32_t n_stages,
-                    int32_t batch, int32_t aux, int32_t frames, int32_t window, float* c_f32, void* c_hi, void* c_lo,
-                    pk_stream_t stream);
+                    int32_t batch, int32_t aux, int32_t frames, int32_t window, const int32_t* frame_lens, float* c_f32,
+                    void* c_hi, void* c_lo, pk_stream_t stream);
 
 /* first_conv (:401-402, :464): x[b,t,r] = w[r] * noise[b,t] + bias[r] for 64 residual channels, written as split
  * planes (batch, t, 64); rows t >= lens[b] are written as zero (lens may be NULL). */
@@ -155,6 +157,8 @@ typedef struct pk_pwg_layer_args {
   const float* bias2;
   float* skip;             /* fp32 (batch, t, 64) running sum of skips */
   int32_t skip_init;       /* 1: overwrite (first layer), 0: accumulate */
+  void* prof;              /* debug: NULL, or device uint64[40] phase-cycle counters accumulated by the kernel
+                              ([0..1] producer, [8..14] MMA issuer, [16..22]/[24..30] epilogue halves, [32] tiles) */
 } pk_pwg_layer_args;
 int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
 

@@ -10,6 +10,8 @@
 //   pk_pwg_upsample       : ConvInUpsampleNet (:201-216) conv_in + [nearest stretch + FIR] x scales, fused per frame.
 //   pk_pwg_first_conv     : first_conv 1 -> R channels (:464).
 //   pk_pwg_tail           : skips * sqrt(1/L) -> ReLU -> 1x1 -> ReLU -> 1x1 (:469-471).
+#include <string.h>
+
 #include <algorithm>
 
 #include "pk_host.h"
@@ -27,7 +29,7 @@ constexpr int kPwgStages = 3;
 constexpr int kPwgTile = 128 * kSwizzleBytes;                 // 16 KB: one plane of a 128-row K-chunk
 constexpr int kPwgStageBytes = 4 * kPwgTile;                  // A hi, A lo, B hi, B lo
 constexpr int kPwgZBytes = 2 * kPwgTile;                      // z hi, z lo
-constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgZBytes + 1024 + 256;
+constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgZBytes + 1024 + 256 + 1024;  // + biases
 constexpr int kPwgEpiWarps = 8;
 constexpr int kPwgThreads = 64 + kPwgEpiWarps * 32;           // 320
 constexpr int kPwgG1Chunks = 5;                               // 3 taps + 2 aux chunks (64 + 16 channels)
@@ -44,7 +46,20 @@ struct PwgLayerArgs {
   const __nv_bfloat16* x_lo;
   __nv_bfloat16* y_hi;          // layer output planes
   __nv_bfloat16* y_lo;
+  unsigned long long* prof;     // optional phase-timing counters (debug), see pk_pwg_layer_args.prof
 };
+
+// phase timing (only when p.prof != NULL): accumulate clock64() deltas per section
+#define PK_TICK(k)                                      \
+  if (p.prof) {                                         \
+    const long long n_ = clock64();                     \
+    tacc[k] += n_ - tlast;                              \
+    tlast = n_;                                         \
+  }
+#define PK_TICK_FLUSH(base, n)                                                              \
+  if (p.prof) {                                                                             \
+    for (int k_ = 0; k_ < (n); ++k_) atomicAdd(p.prof + (base) + k_, static_cast<unsigned long long>(tacc[k_])); \
+  }
 
 struct PwgTileIter {
   int idx, step, tiles_per_b, total, t;
@@ -74,18 +89,20 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
                  const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                  const PwgLayerArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* z_smem = smem + kPwgStages * kPwgStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(z_smem + kPwgZBytes);
-  uint64_t* full_bar = bars;                       // [stages]
-  uint64_t* empty_bar = full_bar + kPwgStages;     // [stages]
-  uint64_t* acc1_full = empty_bar + kPwgStages;    // [2]
-  uint64_t* acc1_empty = acc1_full + 2;            // [2]
-  uint64_t* acc2_full = acc1_empty + 2;            // [2]
-  uint64_t* acc2_empty = acc2_full + 2;            // [2]
-  uint64_t* z_full = acc2_empty + 2;               // [1]
-  uint64_t* z_empty = z_full + 1;                  // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 1);
+  // all shared-memory accesses go through 32-bit shared-space addresses (see pk_sm100.cuh)
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-B aligned for SWIZZLE_128B
+  const uint32_t z_smem = smem + kPwgStages * kPwgStageBytes;
+  const uint32_t bars = z_smem + kPwgZBytes;
+  const uint32_t full_bar = bars;                       // [stages]
+  const uint32_t empty_bar = full_bar + 8 * kPwgStages; // [stages]
+  const uint32_t acc1_full = empty_bar + 8 * kPwgStages;  // [2]
+  const uint32_t acc1_empty = acc1_full + 16;           // [2]
+  const uint32_t acc2_full = acc1_empty + 16;           // [2]
+  const uint32_t acc2_empty = acc2_full + 16;           // [2]
+  const uint32_t z_full = acc2_empty + 16;              // [1]
+  const uint32_t z_empty = z_full + 8;                  // [1]
+  const uint32_t tmem_slot = z_empty + 8;
+  const uint32_t s_bias = z_smem + kPwgZBytes + 256;    // float[256]: bias1 | bias2
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,50 +110,61 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_c_hi); tma_prefetch_desc(&tm_c_lo);
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w1_lo); tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo);
-    for (int s = 0; s < kPwgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kPwgStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], kPwgEpiWarps * 32);
-      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], kPwgEpiWarps * 32);
+      mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, kPwgEpiWarps * 32);
+      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, kPwgEpiWarps * 32);
     }
-    mbar_init(z_full, kPwgEpiWarps * 32);
-    mbar_init(z_empty, 1);
+    mbar_init_a(z_full, kPwgEpiWarps * 32);
+    mbar_init_a(z_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_a<512>(tmem_slot);
+  if (threadIdx.x >= 64) {
+    const int i = threadIdx.x - 64;
+    sts_f32(s_bias + 4 * i, i < 128 ? p.bias1[i] : p.bias2[i - 128]);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds_u32(tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ TMA producer ------------------------------
       uint32_t it = 0;  // running stage counter
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tlast = clock64();
       auto load_g1 = [&](int b, int m0) {
         for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
           const int s = it % kPwgStages;
-          mbar_wait(&empty_bar[s], ((it / kPwgStages) & 1) ^ 1);
-          uint8_t* st = smem + s * kPwgStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], kPwgStageBytes);
+          PK_TICK(1)
+          mbar_wait_a(empty_bar + 8 * s, ((it / kPwgStages) & 1) ^ 1);
+          PK_TICK(0)
+          const uint32_t st = smem + s * kPwgStageBytes;
+          const uint32_t fb = full_bar + 8 * s;
+          mbar_arrive_expect_tx_a(fb, kPwgStageBytes);
           if (j < 3) {
             const int row = m0 + (j - 1) * p.dil;
-            tma_load_3d(st, &tm_x_hi, &full_bar[s], 0, row, b);
-            tma_load_3d(st + kPwgTile, &tm_x_lo, &full_bar[s], 0, row, b);
+            tma_load_3d_a(st, &tm_x_hi, fb, 0, row, b);
+            tma_load_3d_a(st + kPwgTile, &tm_x_lo, fb, 0, row, b);
           } else {
-            tma_load_3d(st, &tm_c_hi, &full_bar[s], (j - 3) * kChunkK, m0, b);
-            tma_load_3d(st + kPwgTile, &tm_c_lo, &full_bar[s], (j - 3) * kChunkK, m0, b);
+            tma_load_3d_a(st, &tm_c_hi, fb, (j - 3) * kChunkK, m0, b);
+            tma_load_3d_a(st + kPwgTile, &tm_c_lo, fb, (j - 3) * kChunkK, m0, b);
           }
-          tma_load_3d(st + 2 * kPwgTile, &tm_w1_hi, &full_bar[s], j * kChunkK, 0, 0);
-          tma_load_3d(st + 3 * kPwgTile, &tm_w1_lo, &full_bar[s], j * kChunkK, 0, 0);
+          tma_load_3d_a(st + 2 * kPwgTile, &tm_w1_hi, fb, j * kChunkK, 0, 0);
+          tma_load_3d_a(st + 3 * kPwgTile, &tm_w1_lo, fb, j * kChunkK, 0, 0);
         }
       };
       auto load_g2 = [&]() {
         const int s = it % kPwgStages;
-        mbar_wait(&empty_bar[s], ((it / kPwgStages) & 1) ^ 1);
-        uint8_t* st = smem + s * kPwgStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], 2 * kPwgTile);
-        tma_load_3d(st + 2 * kPwgTile, &tm_w2_hi, &full_bar[s], 0, 0, 0);
-        tma_load_3d(st + 3 * kPwgTile, &tm_w2_lo, &full_bar[s], 0, 0, 0);
+        PK_TICK(1)
+        mbar_wait_a(empty_bar + 8 * s, ((it / kPwgStages) & 1) ^ 1);
+        PK_TICK(0)
+        const uint32_t st = smem + s * kPwgStageBytes;
+        mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kPwgTile);
+        tma_load_3d_a(st + 2 * kPwgTile, &tm_w2_hi, full_bar + 8 * s, 0, 0, 0);
+        tma_load_3d_a(st + 3 * kPwgTile, &tm_w2_lo, full_bar + 8 * s, 0, 0, 0);
         ++it;
       };
       PwgTileIter ti(p);
@@ -149,6 +177,8 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
         load_g2();
         have = have_next; b = nb; m0 = nm0;
       }
+      PK_TICK(1)
+      PK_TICK_FLUSH(0, 2)
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -156,6 +186,8 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, 128);
       const int aux_tail_ksteps = ((p.aux_ch - kChunkK) + kUmmaK - 1) / kUmmaK;  // k-steps in the 2nd aux chunk
       uint32_t it = 0;
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tlast = clock64();
       auto mma_chunk = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int ksteps, bool first) {
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
@@ -166,34 +198,42 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       };
       auto g1 = [&](int i) {
         const int buf = i & 1;
-        mbar_wait(&acc1_empty[buf], ((i >> 1) & 1) ^ 1);
+        PK_TICK(6)
+        mbar_wait_a(acc1_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+        PK_TICK(0)
         tcgen05_fence_after();
         const uint32_t d = tmem_base + buf * 128;
         for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
           const int s = it % kPwgStages;
-          mbar_wait(&full_bar[s], (it / kPwgStages) & 1);
+          PK_TICK(2)
+          mbar_wait_a(full_bar + 8 * s, (it / kPwgStages) & 1);
+          PK_TICK(1)
           tcgen05_fence_after();
-          const uint32_t st = smem_u32(smem + s * kPwgStageBytes);
+          const uint32_t st = smem + s * kPwgStageBytes;
           mma_chunk(d, make_smem_desc_sw128(st), make_smem_desc_sw128(st + kPwgTile), make_smem_desc_sw128(st + 2 * kPwgTile),
                     make_smem_desc_sw128(st + 3 * kPwgTile), j == kPwgG1Chunks - 1 ? aux_tail_ksteps : 4, j == 0);
-          umma_commit(&empty_bar[s]);
+          umma_commit_a(empty_bar + 8 * s);
         }
-        umma_commit(&acc1_full[buf]);
+        umma_commit_a(acc1_full + 8 * buf);
       };
       auto g2 = [&](int i) {
         const int buf = i & 1;
-        mbar_wait(z_full, i & 1);
-        mbar_wait(&acc2_empty[buf], ((i >> 1) & 1) ^ 1);
+        PK_TICK(2)
+        mbar_wait_a(z_full, i & 1);
+        PK_TICK(3)
+        mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+        PK_TICK(4)
         const int s = it % kPwgStages;
-        mbar_wait(&full_bar[s], (it / kPwgStages) & 1);
+        mbar_wait_a(full_bar + 8 * s, (it / kPwgStages) & 1);
+        PK_TICK(5)
         tcgen05_fence_after();
-        const uint32_t st = smem_u32(smem + s * kPwgStageBytes);
-        const uint32_t zs = smem_u32(z_smem);
+        const uint32_t st = smem + s * kPwgStageBytes;
+        const uint32_t zs = z_smem;
         mma_chunk(tmem_base + 256 + buf * 128, make_smem_desc_sw128(zs), make_smem_desc_sw128(zs + kPwgTile),
                   make_smem_desc_sw128(st + 2 * kPwgTile), make_smem_desc_sw128(st + 3 * kPwgTile), 4, true);
-        umma_commit(&empty_bar[s]);
-        umma_commit(z_empty);
-        umma_commit(&acc2_full[buf]);
+        umma_commit_a(empty_bar + 8 * s);
+        umma_commit_a(z_empty);
+        umma_commit_a(acc2_full + 8 * buf);
         ++it;
       };
       PwgTileIter ti(p);
@@ -208,6 +248,9 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
         g2(n_done++);
         have = have_next;
       }
+      PK_TICK(6)
+      PK_TICK_FLUSH(8, 7)
+      if (p.prof) atomicAdd(p.prof + 32, static_cast<unsigned long long>(n_done));
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
@@ -217,14 +260,42 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
     const int r = quarter * 32 + lane;  // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const float kSqrtHalf = 0.70710678118654752440f;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
     PwgTileIter ti(p);
     int b, m0;
     for (int i = 0; ti.next(b, m0); ++i) {
       const int buf = i & 1;
       const int t = m0 + r;
       const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
+      // ---- prefetch E2's global operands (coalesced, in the transposed mapping used by the store phase) ----
+      const int c8 = lane & 7;              // 16-byte chunk (4 fp32 columns) handled in the transposed phase
+      const int rsub = lane >> 3;           // row within a group of 4
+      const int row_base = m0 + quarter * 32;
+      uint4 pre[16];                        // half 0: old skip (float4) [pass][k]; half 1: {x_hi.xy, x_lo.xy} [pass][k]
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int tt = row_base + 4 * k + rsub;
+          const long long off = (static_cast<long long>(b) * p.t + tt) * 64 + pass * 32 + 4 * c8;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (tt < p.t) {
+            if (half == 0) {
+              if (!p.skip_init) v = *reinterpret_cast<const uint4*>(p.skip + off);
+            } else {
+              const uint2 xh = __ldg(reinterpret_cast<const uint2*>(p.x_hi + off));
+              const uint2 xl = __ldg(reinterpret_cast<const uint2*>(p.x_lo + off));
+              v = make_uint4(xh.x, xh.y, xl.x, xl.y);
+            }
+          }
+          pre[pass * 8 + k] = v;
+        }
+      }
       // ---- E1: gate ----
-      mbar_wait(&acc1_full[buf], (i >> 1) & 1);
+      PK_TICK(6)
+      mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
+      PK_TICK(0)
       tcgen05_fence_after();
       float va[32], vb[32];
       __syncwarp();
@@ -232,26 +303,33 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&acc1_empty[buf]);
+      mbar_arrive_a(acc1_empty + 8 * buf);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float a = va[j] + __ldg(p.bias1 + half * 32 + j);
-        const float g = vb[j] + __ldg(p.bias1 + 64 + half * 32 + j);
-        va[j] = fast_tanh(a) * fast_sigmoid(g);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 ba = lds_f4(s_bias + 4 * (half * 32 + j));
+        const float4 bg = lds_f4(s_bias + 4 * (64 + half * 32 + j));
+        va[j + 0] = fast_tanh(va[j + 0] + ba.x) * fast_sigmoid(vb[j + 0] + bg.x);
+        va[j + 1] = fast_tanh(va[j + 1] + ba.y) * fast_sigmoid(vb[j + 1] + bg.y);
+        va[j + 2] = fast_tanh(va[j + 2] + ba.z) * fast_sigmoid(vb[j + 2] + bg.z);
+        va[j + 3] = fast_tanh(va[j + 3] + ba.w) * fast_sigmoid(vb[j + 3] + bg.w);
       }
-      mbar_wait(z_empty, (i & 1) ^ 1);  // GEMM2 of the previous tile has finished reading z
+      PK_TICK(1)
+      mbar_wait_a(z_empty, (i & 1) ^ 1);  // GEMM2 of the previous tile has finished reading z
+      PK_TICK(2)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 h, l;
         split8(va + 8 * q, h, l);
         const int chunk = (half * 4 + q) ^ (r & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-        *reinterpret_cast<uint4*>(z_smem + r * kSwizzleBytes + chunk * 16) = h;
-        *reinterpret_cast<uint4*>(z_smem + kPwgTile + r * kSwizzleBytes + chunk * 16) = l;
+        sts_u4(z_smem + r * kSwizzleBytes + chunk * 16, h);
+        sts_u4(z_smem + kPwgTile + r * kSwizzleBytes + chunk * 16, l);
       }
       fence_proxy_async_smem();
-      mbar_arrive(z_full);
+      mbar_arrive_a(z_full);
       // ---- E2: skip / residual ----
-      mbar_wait(&acc2_full[buf], (i >> 1) & 1);
+      PK_TICK(3)
+      mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
+      PK_TICK(4)
       tcgen05_fence_after();
       float v0[32], v1[32];
       __syncwarp();
@@ -259,52 +337,61 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64 + 32, v1);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&acc2_empty[buf]);
-      if (t < p.t) {
-        const long long row_off = (static_cast<long long>(b) * p.t + t) * 64;
-        if (half == 0) {
-          // skip accumulation (fp32)
-          float4* sp = reinterpret_cast<float4*>(p.skip + row_off);
+      mbar_arrive_a(acc2_empty + 8 * buf);
+      // Transpose through shared memory so that global traffic is coalesced: each warp stages 32 rows x 32 fp32
+      // columns in a private 4 KB slice of the (now idle) z buffer - quarter q owns rows 32q..32q+31 of both z planes,
+      // its two warps take one plane each - then re-reads it with 8 lanes per row (4 rows x 128 B per instruction).
+      {
+        const uint32_t slice = z_smem + half * kPwgTile + quarter * 32 * kSwizzleBytes;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float* v = q < 8 ? v0 + 4 * q : v1 + 4 * (q - 8);
-            float4 acc = make_float4(v[0] + __ldg(p.bias2 + 4 * q), v[1] + __ldg(p.bias2 + 4 * q + 1),
-                                     v[2] + __ldg(p.bias2 + 4 * q + 2), v[3] + __ldg(p.bias2 + 4 * q + 3));
-            if (!p.skip_init) {
-              const float4 o = sp[q];
-              acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-            }
-            sp[q] = acc;
+        for (int pass = 0; pass < 2; ++pass) {
+          const float* v = pass == 0 ? v0 : v1;
+          const uint32_t bias = s_bias + 4 * (128 + half * 64 + pass * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 bb = lds_f4(bias + 16 * c);
+            sts_f4(slice + lane * kSwizzleBytes + ((c ^ (lane & 7)) << 4),
+                   make_float4(v[4 * c] + bb.x, v[4 * c + 1] + bb.y, v[4 * c + 2] + bb.z, v[4 * c + 3] + bb.w));
           }
-        } else {
-          // residual: x_out = (out + b_out + x_in) * sqrt(0.5); rows past the utterance end stay zero
-          const uint4* xh = reinterpret_cast<const uint4*>(p.x_hi + row_off);
-          const uint4* xl = reinterpret_cast<const uint4*>(p.x_lo + row_off);
-          uint4* yh = reinterpret_cast<uint4*>(p.y_hi + row_off);
-          uint4* yl = reinterpret_cast<uint4*>(p.y_lo + row_off);
-          const bool live = t < len;
+          __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float* v = q < 4 ? v0 + 8 * q : v1 + 8 * (q - 4);
-            const uint4 h4 = __ldg(xh + q), l4 = __ldg(xl + q);
-            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
-            const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
-            float o[8];
+          for (int k = 0; k < 8; ++k) {
+            const int rl = 4 * k + rsub;
+            const int tt = row_base + rl;
+            const float4 o = lds_f4(slice + rl * kSwizzleBytes + ((c8 ^ (rl & 7)) << 4));
+            if (tt < p.t) {
+              const long long off = (static_cast<long long>(b) * p.t + tt) * 64 + pass * 32 + 4 * c8;
+              if (half == 0) {
+                const uint4 old = pre[pass * 8 + k];   // zeros when skip_init
+                *reinterpret_cast<float4*>(p.skip + off) =
+                    make_float4(o.x + __uint_as_float(old.x), o.y + __uint_as_float(old.y), o.z + __uint_as_float(old.z),
+                                o.w + __uint_as_float(old.w));
+              } else {
+                const uint2 xh = make_uint2(pre[pass * 8 + k].x, pre[pass * 8 + k].y);
+                const uint2 xl = make_uint2(pre[pass * 8 + k].z, pre[pass * 8 + k].w);
+                const bool live = tt < len;
+                float y[4];
+                y[0] = (o.x + bf16_bits_to_float(xh.x & 0xffffu) + bf16_bits_to_float(xl.x & 0xffffu)) * kSqrtHalf;
+                y[1] = (o.y + bf16_bits_to_float(xh.x >> 16) + bf16_bits_to_float(xl.x >> 16)) * kSqrtHalf;
+                y[2] = (o.z + bf16_bits_to_float(xh.y & 0xffffu) + bf16_bits_to_float(xl.y & 0xffffu)) * kSqrtHalf;
+                y[3] = (o.w + bf16_bits_to_float(xh.y >> 16) + bf16_bits_to_float(xl.y >> 16)) * kSqrtHalf;
+                __nv_bfloat16 h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x0 = bf16_bits_to_float(hw[e] & 0xffffu) + bf16_bits_to_float(lw[e] & 0xffffu);
-              const float x1 = bf16_bits_to_float(hw[e] >> 16) + bf16_bits_to_float(lw[e] >> 16);
-              o[2 * e] = live ? (v[2 * e] + __ldg(p.bias2 + 64 + 8 * q + 2 * e) + x0) * kSqrtHalf : 0.f;
-              o[2 * e + 1] = live ? (v[2 * e + 1] + __ldg(p.bias2 + 64 + 8 * q + 2 * e + 1) + x1) * kSqrtHalf : 0.f;
+                for (int e = 0; e < 4; ++e) split_bf16(live ? y[e] : 0.f, h[e], l[e]);
+                *reinterpret_cast<uint2*>(p.y_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                *reinterpret_cast<uint2*>(p.y_lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+              }
             }
-            uint4 oh, ol;
-            split8(o, oh, ol);
-            yh[q] = oh;
-            yl[q] = ol;
           }
+          __syncwarp();
         }
+        // both warps of this quarter must be done with their slices before either writes the next z tile into them
+        PK_TICK(5)
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
       }
     }
+    PK_TICK(6)
+    if (lane == 0 && quarter == 0) { PK_TICK_FLUSH(16 + half * 8, 7) }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -319,40 +406,40 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
 // grid = (frames, batch); one CTA produces the hop = prod(scales) output samples of one frame for all channels.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kUpMaxStages = 4;
-constexpr int kUpMaxTaps = 33;
+constexpr int kUpMaxScale = 16;
 struct UpsampleArgs {
   int n_stages;
   int scale[kUpMaxStages];
-  float fir[kUpMaxStages][kUpMaxTaps];
+  // polyphase form of "nearest stretch by s, then FIR w[0..2s] with zero padding s":
+  //   out[s*m + r] = sum_{k=0..2} poly[k][r] * in[m - 1 + k],  poly[k][r] = sum_{q : floor((r+q)/s) == k} w[q]
+  float poly[kUpMaxStages][3][kUpMaxScale];
   int aux, frames, window;       // channels, T' (after conv_in), aux_context_window
   int hop;
 };
 
+__device__ __forceinline__ int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
 __global__ void __launch_bounds__(256)
 pwg_upsample_kernel(const float* __restrict__ mel,        // (B, aux, frames + 2*window) channel-first, like the reference
                     const float* __restrict__ w_in,       // conv_in weight [aux][aux][2*window+1]
+                    const int32_t* __restrict__ frame_lens, // valid frames per utterance or NULL
                     const UpsampleArgs a, float* __restrict__ c_f32 /* (B, aux, T) or NULL */,
                     __nv_bfloat16* __restrict__ c_hi, __nv_bfloat16* __restrict__ c_lo /* (B, T, aux) or NULL */) {
   extern __shared__ float up_smem[];
   const int j = blockIdx.x, b = blockIdx.y;
   const int aux = a.aux;
-  // Per-stage ranges needed to produce outputs [lo_out, hi_out) of the last stage, walked backwards.
-  // stage k output index range [lo[k], hi[k]) (may stick out of the valid range; such values are zero).
+  const int n_frames = frame_lens ? min(__ldg(frame_lens + b), a.frames) : a.frames;
+  // stage k output index range [lo[k], hi[k]) needed for outputs [j*hop, (j+1)*hop) of the last stage
   int lo[kUpMaxStages + 1], hi[kUpMaxStages + 1], len[kUpMaxStages + 1];
-  len[0] = a.frames;
+  len[0] = n_frames;
   for (int k = 0; k < a.n_stages; ++k) len[k + 1] = len[k] * a.scale[k];
   lo[a.n_stages] = j * a.hop;
   hi[a.n_stages] = (j + 1) * a.hop;
   for (int k = a.n_stages - 1; k >= 0; --k) {
     const int s = a.scale[k];
-    // y[t] = sum_q w[q] * u[t + q - s], u[i] = in[floor(i / s)] for 0 <= i < s*len[k] else 0
-    int l = lo[k + 1] - s, h = hi[k + 1] - 1 + s;   // u index range (inclusive h)
-    l = l < 0 ? -((-l + s - 1) / s) : l / s;
-    h = h < 0 ? -((-h + s - 1) / s) : h / s;
-    lo[k] = l;
-    hi[k] = h + 1;
+    lo[k] = floordiv(lo[k + 1], s) - 1;
+    hi[k] = floordiv(hi[k + 1] - 1, s) + 2;
   }
-  // smem layout: stage k buffer [aux][hi[k]-lo[k]]
   float* buf[kUpMaxStages + 1];
   int width[kUpMaxStages + 1];
   {
@@ -365,11 +452,11 @@ pwg_upsample_kernel(const float* __restrict__ mel,        // (B, aux, frames + 2
   }
   const int kin = 2 * a.window + 1;
   const int mel_len = a.frames + 2 * a.window;
-  // stage 0: conv_in outputs m[ch][f] for f in [lo[0], hi[0]) (zero outside [0, frames))
+  // stage 0: conv_in outputs m[ch][f] for f in [lo[0], hi[0]) (zero outside [0, n_frames))
   for (int idx = threadIdx.x; idx < aux * width[0]; idx += blockDim.x) {
     const int ch = idx / width[0], f = lo[0] + idx % width[0];
     float acc = 0.f;
-    if (f >= 0 && f < a.frames) {
+    if (f >= 0 && f < n_frames) {
       const float* mp = mel + (static_cast<long long>(b) * aux) * mel_len + f;
       const float* wp = w_in + static_cast<long long>(ch) * aux * kin;
       for (int ci = 0; ci < aux; ++ci)
@@ -378,36 +465,59 @@ pwg_upsample_kernel(const float* __restrict__ mel,        // (B, aux, frames + 2
     buf[0][idx] = acc;
   }
   __syncthreads();
-  for (int k = 0; k < a.n_stages; ++k) {
-    const int s = a.scale[k], taps = 2 * s + 1;
-    const int ulen = s * len[k];
-    const bool last = (k == a.n_stages - 1);
+  for (int k = 0; k + 1 < a.n_stages; ++k) {   // intermediate stages stay in shared memory
+    const int s = a.scale[k];
     for (int idx = threadIdx.x; idx < aux * width[k + 1]; idx += blockDim.x) {
-      // for the last stage iterate channel-fastest so the channels-last global store is coalesced
-      const int ch = last ? idx % aux : idx / width[k + 1];
-      const int tt = last ? idx / aux : idx % width[k + 1];
+      const int ch = idx / width[k + 1], tt = idx % width[k + 1];
       const int t = lo[k + 1] + tt;
       float acc = 0.f;
       if (t >= 0 && t < len[k + 1]) {
-        for (int q = 0; q < taps; ++q) {
-          const int ui = t + q - s;
-          if (ui >= 0 && ui < ulen) acc = fmaf(a.fir[k][q], buf[k][ch * width[k] + (ui / s - lo[k])], acc);
-        }
+        const int m = t / s, r = t - m * s;
+        const float* in = buf[k] + ch * width[k] + (m - 1 - lo[k]);   // in[-1], in[0], in[+1] are all inside the buffer
+        acc = a.poly[k][0][r] * in[0];
+        acc = fmaf(a.poly[k][1][r], in[1], acc);
+        acc = fmaf(a.poly[k][2][r], in[2], acc);
       }
-      if (!last) {
-        buf[k + 1][ch * width[k + 1] + tt] = acc;
-      } else {
-        const long long T = len[k + 1];
-        if (c_f32) c_f32[(static_cast<long long>(b) * aux + ch) * T + t] = acc;
-        if (c_hi) {
-          __nv_bfloat16 h, l;
-          split_bf16(acc, h, l);
-          c_hi[(static_cast<long long>(b) * T + t) * aux + ch] = h;
-          c_lo[(static_cast<long long>(b) * T + t) * aux + ch] = l;
-        }
-      }
+      buf[k + 1][idx] = acc;
     }
     __syncthreads();
+  }
+  {
+    // last stage: one thread per (sample, group of 8 channels) so the channels-last store is 16-byte vectorised
+    const int k = a.n_stages - 1;
+    const int s = a.scale[k];
+    const long long T = static_cast<long long>(a.frames) * a.hop;  // row pitch of the (padded) batch
+    const int groups = (aux + 7) / 8;
+    for (int idx = threadIdx.x; idx < a.hop * groups; idx += blockDim.x) {
+      const int g = idx % groups, tt = idx / groups;
+      const int t = lo[k + 1] + tt;
+      const bool live = t < len[k + 1];
+      const int m = t / s, r = t - m * s;
+      const float p0 = a.poly[k][0][r], p1 = a.poly[k][1][r], p2 = a.poly[k][2][r];
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = g * 8 + e;
+        float acc = 0.f;
+        if (live && ch < aux) {
+          const float* in = buf[k] + ch * width[k] + (m - 1 - lo[k]);
+          acc = fmaf(p2, in[2], fmaf(p1, in[1], p0 * in[0]));
+        }
+        v[e] = acc;
+      }
+      if (c_f32) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (g * 8 + e < aux) c_f32[(static_cast<long long>(b) * aux + g * 8 + e) * T + t] = v[e];
+      }
+      if (c_hi) {
+        uint4 h, l;
+        split8(v, h, l);
+        const long long o = (static_cast<long long>(b) * T + t) * aux + g * 8;
+        *reinterpret_cast<uint4*>(c_hi + o) = h;   // aux % 8 == 0 is enforced by the host wrapper
+        *reinterpret_cast<uint4*>(c_lo + o) = l;
+      }
+    }
   }
 }
 
@@ -439,9 +549,9 @@ __global__ void __launch_bounds__(256)
 pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ w1 /*[64][64] out,in*/, const float* __restrict__ b1,
                 const float* __restrict__ w2 /*[64]*/, const float* __restrict__ b2, float scale, long long rows,
                 float* __restrict__ out) {
-  __shared__ float sw1[64 * 65];
+  __shared__ float4 sw1[64 * 16];
   __shared__ float sb1[64], sw2[64];
-  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) sw1[(i / 64) * 65 + (i % 64)] = w1[i];
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw1[i] = reinterpret_cast<const float4*>(w1)[i];
   if (threadIdx.x < 64) { sb1[threadIdx.x] = b1[threadIdx.x]; sw2[threadIdx.x] = w2[threadIdx.x]; }
   __syncthreads();
   const float bias2 = __ldg(b2);
@@ -456,11 +566,18 @@ pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ w1 /*[
       s[4 * q + 2] = fmaxf(v.z * scale, 0.f); s[4 * q + 3] = fmaxf(v.w * scale, 0.f);
     }
     float y = bias2;
+#pragma unroll 2
     for (int o = 0; o < 64; ++o) {
-      float acc = sb1[o];
+      float acc0 = sb1[o], acc1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 64; ++k) acc = fmaf(sw1[o * 65 + k], s[k], acc);
-      y = fmaf(sw2[o], fmaxf(acc, 0.f), y);
+      for (int k = 0; k < 16; k += 2) {
+        const float4 wa = sw1[o * 16 + k], wb = sw1[o * 16 + k + 1];   // warp-uniform address: broadcast
+        acc0 = fmaf(wa.x, s[4 * k], acc0); acc0 = fmaf(wa.y, s[4 * k + 1], acc0);
+        acc0 = fmaf(wa.z, s[4 * k + 2], acc0); acc0 = fmaf(wa.w, s[4 * k + 3], acc0);
+        acc1 = fmaf(wb.x, s[4 * k + 4], acc1); acc1 = fmaf(wb.y, s[4 * k + 5], acc1);
+        acc1 = fmaf(wb.z, s[4 * k + 6], acc1); acc1 = fmaf(wb.w, s[4 * k + 7], acc1);
+      }
+      y = fmaf(sw2[o], fmaxf(acc0 + acc1, 0.f), y);
     }
     out[row] = y;
   }
@@ -504,6 +621,7 @@ extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t str
   p.lens = a->lens; p.bias1 = a->bias1; p.bias2 = a->bias2; p.skip = a->skip; p.skip_init = a->skip_init;
   p.x_hi = static_cast<const __nv_bfloat16*>(a->x_hi); p.x_lo = static_cast<const __nv_bfloat16*>(a->x_lo);
   p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  p.prof = static_cast<unsigned long long*>(a->prof);
   const int grid = std::min(p.total_tiles, sm_count());
   pwg_layer_kernel<<<grid, kPwgThreads, kPwgSmem, static_cast<cudaStream_t>(stream)>>>(tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi, tw1_lo,
                                                                                         tw2_hi, tw2_lo, p);
@@ -513,33 +631,34 @@ extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t str
 }
 
 extern "C" int pk_pwg_upsample(const float* mel, const float* conv_in_w, const float* fir, const int32_t* scales,
-                               int32_t n_stages, int32_t batch, int32_t aux, int32_t frames, int32_t window, float* c_f32,
-                               void* c_hi, void* c_lo, pk_stream_t stream) {
+                               int32_t n_stages, int32_t batch, int32_t aux, int32_t frames, int32_t window,
+                               const int32_t* frame_lens, float* c_f32, void* c_hi, void* c_lo, pk_stream_t stream) {
   using namespace pk;
   PK_CHECK_ARG(mel && conv_in_w && fir && scales, "NULL pointer");
   PK_CHECK_ARG(n_stages >= 1 && n_stages <= kUpMaxStages, "n_stages must be in [1,%d]", kUpMaxStages);
   PK_CHECK_ARG(batch > 0 && aux > 0 && frames > 0 && window >= 0, "bad sizes");
   PK_CHECK_ARG(c_f32 || c_hi, "no output requested");
   PK_CHECK_ARG((c_hi == nullptr) == (c_lo == nullptr), "c_hi and c_lo must both be set or both NULL");
+  PK_CHECK_ARG(c_hi == nullptr || (aux % 8) == 0, "split-plane output needs aux %% 8 == 0");
   UpsampleArgs a;
+  memset(&a, 0, sizeof(a));
   a.n_stages = n_stages; a.aux = aux; a.frames = frames; a.window = window; a.hop = 1;
   for (int k = 0; k < n_stages; ++k) {
-    PK_CHECK_ARG(scales[k] >= 1 && 2 * scales[k] + 1 <= kUpMaxTaps, "upsample scale %d unsupported", scales[k]);
-    a.scale[k] = scales[k];
-    a.hop *= scales[k];
-    for (int q = 0; q < 2 * scales[k] + 1; ++q) a.fir[k][q] = *fir++;  // host pointer (tiny FIRs, concatenated)
+    const int s = scales[k];
+    PK_CHECK_ARG(s >= 1 && s <= kUpMaxScale, "upsample scale %d unsupported (max %d)", s, kUpMaxScale);
+    a.scale[k] = s;
+    a.hop *= s;
+    for (int r = 0; r < s; ++r)
+      for (int q = 0; q < 2 * s + 1; ++q) a.poly[k][(r + q) / s][r] += fir[q];  // host pointer (tiny FIRs, concatenated)
+    fir += 2 * s + 1;
   }
-  // smem: sum over stages of aux * width; widths bounded by hop_k + 2 (+halo)
   size_t floats = 0;
   {
-    int lo = 0, hi = a.hop;
-    int w[kUpMaxStages + 1];
-    w[n_stages] = hi - lo;
+    int w = a.hop;
     for (int k = n_stages - 1; k >= 0; --k) {
-      const int s = a.scale[k];
-      w[k] = (w[k + 1] + 2 * s) / s + 2;
+      w = (w - 1) / a.scale[k] + 4;          // upper bound of hi[k] - lo[k]
+      floats += static_cast<size_t>(aux) * w;
     }
-    for (int k = 0; k < n_stages; ++k) floats += static_cast<size_t>(aux) * (w[k] + 2);
   }
   const size_t smem = floats * sizeof(float);
   PK_CHECK_ARG(smem <= 200 * 1024, "upsample tile does not fit shared memory (%zu bytes)", smem);
@@ -549,7 +668,7 @@ extern "C" int pk_pwg_upsample(const float* mel, const float* conv_in_w, const f
     attr_smem = smem;
   }
   dim3 grid(frames, batch);
-  pwg_upsample_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(mel, conv_in_w, a, c_f32,
+  pwg_upsample_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(mel, conv_in_w, frame_lens, a, c_f32,
                                                                               static_cast<__nv_bfloat16*>(c_hi),
                                                                               static_cast<__nv_bfloat16*>(c_lo));
   PK_CHECK_CUDA(cudaGetLastError());

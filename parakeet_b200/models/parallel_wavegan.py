@@ -28,7 +28,7 @@ def _declare():
         return
     L = _lib.lib()
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
-    L.pk_pwg_upsample.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.pk_pwg_upsample.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.pk_pwg_first_conv.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     L.pk_pwg_residual_layer.argtypes = [C.POINTER(PwgLayerArgs), vp]
     L.pk_pwg_tail.argtypes = [vp, vp, vp, vp, vp, f32, i64, vp, vp]
@@ -42,7 +42,7 @@ class PwgLayerArgs(C.Structure):
                 ("lens", C.c_void_p), ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p),
                 ("y_lo", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("w1_hi", C.c_void_p),
                 ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p), ("bias1", C.c_void_p),
-                ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32)]
+                ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
 
 
 def _split_host(w, device):
@@ -230,12 +230,14 @@ class PWGGenerator(Layer):
         x = x.contiguous().float()
         c = c.contiguous().float()
         lens_p = _ptr(lens) if lens is not None else None
+        frame_lens = None
         if lens is not None:
             assert lens.dtype == torch.int32 and lens.is_cuda
+            frame_lens = torch.div(lens, self.upsample_factor, rounding_mode="floor").to(torch.int32)
         _lib.check(L.pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]), pk["fir_host"].ctypes.data_as(C.c_void_p),
                                      pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
-                                     self.aux_channels, frames, self.aux_context_window, None, _ptr(ws["c"].hi),
-                                     _ptr(ws["c"].lo), st), "pk_pwg_upsample")
+                                     self.aux_channels, frames, self.aux_context_window, _ptr(frame_lens), None,
+                                     _ptr(ws["c"].hi), _ptr(ws["c"].lo), st), "pk_pwg_upsample")
         _lib.check(L.pk_pwg_first_conv(_ptr(x), _ptr(pk["first_w"]), _ptr(pk["first_b"]), lens_p, B, T, _ptr(ws["xa"].hi),
                                        _ptr(ws["xa"].lo), st), "pk_pwg_first_conv")
         if lens is not None:
@@ -247,6 +249,7 @@ class PWGGenerator(Layer):
         args.lens = lens.data_ptr() if lens is not None else None
         args.c_hi, args.c_lo = ws["c"].hi.data_ptr(), ws["c"].lo.data_ptr()
         args.skip = ws["skip"].data_ptr()
+        args.prof = self._prof.data_ptr() if getattr(self, "_prof", None) is not None else None
         for i, lay in enumerate(pk["layers"]):
             args.dilation = lay["dil"]
             args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
@@ -272,8 +275,8 @@ class PWGGenerator(Layer):
         _lib.check(_lib.lib().pk_pwg_upsample(_ptr(c.contiguous().float()), _ptr(pk["conv_in_w"]),
                                               pk["fir_host"].ctypes.data_as(C.c_void_p),
                                               pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
-                                              self.aux_channels, frames, self.aux_context_window, _ptr(out), None, None,
-                                              _stream()), "pk_pwg_upsample")
+                                              self.aux_channels, frames, self.aux_context_window, None, _ptr(out), None,
+                                              None, _stream()), "pk_pwg_upsample")
         return out
 
     def inference(self, c=None, x=None):
