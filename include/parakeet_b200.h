@@ -167,6 +167,47 @@ int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
 int pk_pwg_tail(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float scale,
                 int64_t rows, float* out, pk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * FastSpeech2 row-wise kernels (reference: parakeet/models/fastspeech2/fastspeech2.py and parakeet/modules/*).
+ * Shapes are (batch, t, channels) channels-last fp32 unless noted.  `lens` (device int32 [batch] or NULL) selects
+ * the "independent utterances" mode used for batched inference: rows t >= lens[b] are written as zero so that every
+ * utterance sees exactly the zero padding it would see alone; with lens == NULL padded rows are computed like any
+ * other row, which is what the reference's batched training forward does.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* Embedding(padding_idx) + ScaledPositionalEncoding (modules/fastspeech2_transformer/embedding.py:46-62,111-126;
+ * encoder.py:103-105): y = (ids ? table[ids] (zeros for padding_idx) : x_in) + alpha[0] * PE. */
+int pk_embed_pe(const int64_t* ids, const float* table, int32_t vocab, int32_t padding_idx, const float* x_in,
+                const float* alpha, const int32_t* lens, int32_t batch, int32_t t, int32_t d, float* y, pk_stream_t stream);
+/* nn.LayerNorm over the last dim (encoder_layer.py:55-56,85,107; encoder.py:143,191; modules/layer_norm.py:47-63).
+ * Outputs: y fp32 and/or split planes (either may be NULL). */
+int pk_layer_norm(const float* x, const float* gamma, const float* beta, float eps, const int32_t* lens, int32_t batch,
+                  int32_t t, int32_t d, float* y, void* y_hi, void* y_lo, pk_stream_t stream);
+/* masked_fill(min) -> softmax -> masked_fill(0) of attention.py:107-119 over keys: s fp32 (batch*heads, rows, ld),
+ * keys >= key_lens[b] and the padding columns [keys, ld) get probability 0; output split planes, same layout. */
+int pk_masked_softmax(const float* s, const int32_t* key_lens, int32_t batch, int32_t heads, int32_t rows, int32_t keys,
+                      int32_t ld, void* p_hi, void* p_lo, pk_stream_t stream);
+/* (batch, t, ld_src)[.., col0 + h*dk + d] -> (batch*heads, dk, ld_dst)[.., d, t] (zero-filled for t in [t, ld_dst)):
+ * the value matrix in K-major form for the P.V product (attention.py:126). */
+int pk_transpose_heads(const void* src_hi, const void* src_lo, int32_t batch, int32_t t, int32_t ld_src, int32_t col0,
+                       int32_t dk, int32_t heads, int32_t ld_dst, void* dst_hi, void* dst_lo, pk_stream_t stream);
+/* DurationPredictor.inference post-op (duration_predictor.py:94-101): d = max(round_half_away(exp(x) - offset), 0),
+ * padded tokens -> 0.  Outputs fp32 and/or int64 (either may be NULL). */
+int pk_duration_post(const float* x, const int32_t* lens, int32_t batch, int32_t t, float offset, float* d_f32, int64_t* d_i64,
+                     pk_stream_t stream);
+/* LengthRegulator.forward alpha != 1 (length_regulator.py:85-88): out = int64(round_half_away(d * alpha)). */
+int pk_duration_scale(const int64_t* d, float alpha, int64_t n, int64_t* out, pk_stream_t stream);
+/* masked_fill(x, pad_mask, 0) for predictor outputs (variance_predictor.py:101-103): x (batch, t, inner) in place. */
+int pk_mask_rows(float* x, const int32_t* lens, int32_t batch, int32_t t, int32_t inner, pk_stream_t stream);
+/* hs + pitch_embed(p) + energy_embed(e) (fastspeech2.py:426-430): Conv1D(1 -> c, k, pad (k-1)/2) on the scalar tracks
+ * pitch / energy (batch, t); wp/we are [c][k] (Paddle [c,1,k]), bp/be [c]. */
+int pk_variance_embed_add(const float* hs, const float* pitch, const float* energy, const float* wp, const float* bp, int32_t kp,
+                          const float* we, const float* be, int32_t ke, const int32_t* lens, int32_t batch, int32_t t, int32_t c,
+                          float* y, pk_stream_t stream);
+/* ZScore.forward / .inverse over the last dim (modules/normalizer.py:18-33): inverse == 0: (x - mu) / sigma,
+ * inverse != 0: x * sigma + mu; n = total elements, c = channels. */
+int pk_zscore(const float* x, const float* mu, const float* sigma, int32_t c, int64_t n, int32_t inverse, float* y,
+              pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

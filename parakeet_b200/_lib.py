@@ -49,6 +49,14 @@ def lib():
     return _lib
 
 
+class PwgLayerArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("dilation", C.c_int32), ("aux_channels", C.c_int32),
+                ("lens", C.c_void_p), ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p),
+                ("y_lo", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("w1_hi", C.c_void_p),
+                ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p), ("bias1", C.c_void_p),
+                ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
+
+
 def _declare(L):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
@@ -57,12 +65,24 @@ def _declare(L):
         "pk_conv_gemm_simt": [C.POINTER(ConvGemmArgs), vp],
         "pk_length_regulator_lens": [vp, i32, i32, vp, vp],
         "pk_length_regulate": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
+        "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "pk_pwg_first_conv": [vp, vp, vp, vp, i32, i32, vp, vp, vp],
+        "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
+        "pk_pwg_tail": [vp, vp, vp, vp, vp, f32, i64, vp, vp],
+        "pk_embed_pe": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
+        "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],
+        "pk_masked_softmax": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        "pk_transpose_heads": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+        "pk_duration_post": [vp, vp, i32, i32, f32, vp, vp, vp],
+        "pk_duration_scale": [vp, f32, i64, vp, vp],
+        "pk_mask_rows": [vp, vp, i32, i32, i32, vp],
+        "pk_variance_embed_add": [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp],
+        "pk_zscore": [vp, vp, vp, i32, i64, i32, vp, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    del f32
 
 
 def check(rc, what=""):

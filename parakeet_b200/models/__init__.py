@@ -1,1 +1,2 @@
+from .fastspeech2 import FastSpeech2, FastSpeech2Inference  # noqa: F401
 from .parallel_wavegan import PWGGenerator, PWGInference  # noqa: F401

@@ -19,30 +19,11 @@ from .. import _lib
 from ..layer import Layer
 from ..ops import Split, _ptr, _stream
 
-_lib_sigs_done = False
+from .._lib import PwgLayerArgs
 
 
 def _declare():
-    global _lib_sigs_done
-    if _lib_sigs_done:
-        return
-    L = _lib.lib()
-    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
-    L.pk_pwg_upsample.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
-    L.pk_pwg_first_conv.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
-    L.pk_pwg_residual_layer.argtypes = [C.POINTER(PwgLayerArgs), vp]
-    L.pk_pwg_tail.argtypes = [vp, vp, vp, vp, vp, f32, i64, vp, vp]
-    for n in ("pk_pwg_upsample", "pk_pwg_first_conv", "pk_pwg_residual_layer", "pk_pwg_tail"):
-        getattr(L, n).restype = C.c_int
-    _lib_sigs_done = True
-
-
-class PwgLayerArgs(C.Structure):
-    _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("dilation", C.c_int32), ("aux_channels", C.c_int32),
-                ("lens", C.c_void_p), ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p),
-                ("y_lo", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("w1_hi", C.c_void_p),
-                ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p), ("bias1", C.c_void_p),
-                ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
+    _lib.lib()
 
 
 def _split_host(w, device):

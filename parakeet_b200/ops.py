@@ -163,4 +163,86 @@ def length_regulate(x, dur, t_out, want_f32=True, want_split=False):
     return y, ys
 
 
-__all__ = ["Split", "pack_weight", "conv_gemm", "batched_matmul_nt", "length_regulate", "length_regulator_lens", "math"]
+# ----------------------------------------------------------------------------------------------------------------
+# FastSpeech2 row-wise kernels
+# ----------------------------------------------------------------------------------------------------------------
+def embed_pe(ids, table, x_in, alpha, lens, padding_idx=0):
+    """Embedding(padding_idx)+ScaledPositionalEncoding (ids given) or ScaledPositionalEncoding only (x_in given)."""
+    if ids is not None:
+        B, T = ids.shape
+        d = table.shape[1]
+        dev = ids.device
+        ids = ids.contiguous()
+    else:
+        B, T, d = x_in.shape
+        dev = x_in.device
+        x_in = x_in.contiguous()
+    y = torch.empty(B, T, d, dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().pk_embed_pe(_ptr(ids), _ptr(table), table.shape[0] if table is not None else 0, padding_idx,
+                                      _ptr(x_in), _ptr(alpha), _ptr(lens), B, T, d, _ptr(y), _stream()), "pk_embed_pe")
+    return y
+
+
+def layer_norm(x, gamma, beta, lens=None, want_f32=False, want_split=True, eps=1e-5):
+    B, T, d = x.shape
+    y = torch.empty_like(x) if want_f32 else None
+    ys = Split.empty((B, T, d), x.device) if want_split else None
+    _lib.check(_lib.lib().pk_layer_norm(_ptr(x), _ptr(gamma), _ptr(beta), eps, _ptr(lens), B, T, d, _ptr(y),
+                                        _ptr(ys.hi) if ys else None, _ptr(ys.lo) if ys else None, _stream()), "pk_layer_norm")
+    return y, ys
+
+
+def masked_softmax(s, key_lens, batch, heads, rows, keys):
+    """s fp32 (batch*heads, rows, ld) -> split planes of the same shape."""
+    ld = s.shape[-1]
+    p = Split.empty(tuple(s.shape), s.device)
+    _lib.check(_lib.lib().pk_masked_softmax(_ptr(s), _ptr(key_lens), batch, heads, rows, keys, ld, _ptr(p.hi), _ptr(p.lo),
+                                            _stream()), "pk_masked_softmax")
+    return p
+
+
+def transpose_heads(src, col0, dk, heads, ld_dst):
+    B, T, ld_src = src.hi.shape
+    dst = Split.empty((B * heads, dk, ld_dst), src.hi.device)
+    _lib.check(_lib.lib().pk_transpose_heads(_ptr(src.hi), _ptr(src.lo), B, T, ld_src, col0, dk, heads, ld_dst, _ptr(dst.hi),
+                                             _ptr(dst.lo), _stream()), "pk_transpose_heads")
+    return dst
+
+
+def duration_post(x, lens, offset=1.0):
+    B, T = x.shape
+    d_f = torch.empty(B, T, dtype=torch.float32, device=x.device)
+    d_i = torch.empty(B, T, dtype=torch.int64, device=x.device)
+    _lib.check(_lib.lib().pk_duration_post(_ptr(x.contiguous()), _ptr(lens), B, T, offset, _ptr(d_f), _ptr(d_i), _stream()),
+               "pk_duration_post")
+    return d_f, d_i
+
+
+def duration_scale(d, alpha):
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().pk_duration_scale(_ptr(d.contiguous()), alpha, d.numel(), _ptr(out), _stream()), "pk_duration_scale")
+    return out
+
+
+def mask_rows_(x, lens):
+    B, T = x.shape[:2]
+    inner = x.numel() // (B * T)
+    _lib.check(_lib.lib().pk_mask_rows(_ptr(x), _ptr(lens), B, T, inner, _stream()), "pk_mask_rows")
+    return x
+
+
+def variance_embed_add(hs, pitch, energy, wp, bp, we, be, lens=None):
+    B, T, c = hs.shape
+    y = torch.empty_like(hs)
+    _lib.check(_lib.lib().pk_variance_embed_add(_ptr(hs), _ptr(pitch.contiguous()), _ptr(energy.contiguous()), _ptr(wp), _ptr(bp),
+                                                wp.shape[-1], _ptr(we), _ptr(be), we.shape[-1], _ptr(lens), B, T, c, _ptr(y),
+                                                _stream()), "pk_variance_embed_add")
+    return y
+
+
+def zscore(x, mu, sigma, inverse=False):
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().pk_zscore(_ptr(x), _ptr(mu), _ptr(sigma), x.shape[-1], x.numel(), 1 if inverse else 0, _ptr(y), _stream()),
+               "pk_zscore")
+    return y
