@@ -231,6 +231,10 @@ class PWGGenerator(Layer):
         args.c_hi, args.c_lo = ws["c"].hi.data_ptr(), ws["c"].lo.data_ptr()
         args.skip = ws["skip"].data_ptr()
         args.prof = self._prof.data_ptr() if getattr(self, "_prof", None) is not None else None
+        ev = getattr(self, "_layer_events", None)
+        if ev is not None:   # bench.py: CUDA events around the 30 residual-layer launches, on the launching stream
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record()
         for i, lay in enumerate(pk["layers"]):
             args.dilation = lay["dil"]
             args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
@@ -240,6 +244,9 @@ class PWGGenerator(Layer):
             args.skip_init = 1 if i == 0 else 0
             _lib.check(L.pk_pwg_residual_layer(C.byref(args), st), "pk_pwg_residual_layer")
             src, dst = dst, src
+        if ev is not None:
+            ev_b.record()
+            ev.append((ev_a, ev_b))
         out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
         _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")

@@ -1,0 +1,167 @@
+"""GPU parity tests of the model-level path (FastSpeech2, Parallel WaveGAN) against the oracle and golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3   # north_star: "within 1e-3 rel fp32" (max-abs error / max-abs reference per tensor)
+
+
+@pytest.fixture(scope="module")
+def pwg(cuda):
+    from oracle import pwg as opwg
+    from parakeet_b200.models import PWGGenerator
+    params = opwg.synth_params(2, weight_norm=True)
+    gen = PWGGenerator(**opwg.DEFAULT_GENERATOR_PARAMS, device=cuda)
+    gen.set_state_dict(params)
+    return gen, opwg.fold_weight_norm(params)
+
+
+@pytest.fixture(scope="module")
+def fs2(cuda):
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    params = ofs.synth_params(1)
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, device=cuda)
+    m.set_state_dict(params)
+    return m, params
+
+
+def test_pwg_golden(cuda, pwg):
+    gen, _ = pwg
+    g = np.load(os.path.join(GOLD, "pwg_small.npz"))
+    y = gen(torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["c"]).to(cuda))
+    assert rel_err(y, torch.from_numpy(g["y"])) < TOL
+
+
+def test_pwg_upsample_and_generator_vs_oracle(cuda, pwg):
+    from oracle import pwg as opwg
+    gen, folded = pwg
+    x, c = opwg.synth_inputs(5, batch=2, mel_frames=40)
+    with torch.no_grad():
+        y_ref, inter = opwg.generator_forward(folded, x, c, return_intermediates=True)
+    assert rel_err(gen.upsample(c.to(cuda)), inter["c_up"]) < 1e-5
+    y = gen(x.to(cuda), c.to(cuda))
+    assert rel_err(gen._last_x.float().transpose(1, 2), inter["x_layers"][-1]) < TOL
+    assert rel_err(y, y_ref) < TOL
+    # reference API: inference(c) with caller-supplied noise (RNG streams cannot match)
+    mel, noise = torch.randn(30, 80), torch.randn(1, 1, 30 * 300)
+    with torch.no_grad():
+        r = opwg.generator_inference(folded, mel, noise)
+    assert rel_err(gen.inference(mel.to(cuda), x=noise.to(cuda)), r) < TOL
+
+
+def test_pwg_ragged_batch_equals_single_utterances(cuda, pwg):
+    from oracle import pwg as opwg
+    gen, folded = pwg
+    frames, hop = [40, 25, 33], 300
+    xs = torch.zeros(3, 1, max(frames) * hop)
+    cs = torch.zeros(3, 80, max(frames) + 4)
+    refs = []
+    for i, f in enumerate(frames):
+        xi, ci = opwg.synth_inputs(10 + i, batch=1, mel_frames=f)
+        xs[i, :, :f * hop], cs[i, :, :f + 4] = xi[0], ci[0]
+        with torch.no_grad():
+            refs.append(opwg.generator_forward(folded, xi, ci)[0])
+    lens = torch.tensor([f * hop for f in frames], dtype=torch.int32, device=cuda)
+    y = gen(xs.to(cuda), cs.to(cuda), lens=lens)
+    for i, f in enumerate(frames):
+        assert rel_err(y[i, :, :f * hop], refs[i]) < TOL
+
+
+def test_pwg_full_size_properties(cuda, pwg):
+    """cfg2 (B=32, 400 frames -> 3.84 M samples): batch independence + determinism + one utterance vs the oracle."""
+    from oracle import pwg as opwg
+    gen, folded = pwg
+    x, c = opwg.synth_inputs(2, batch=32, mel_frames=400)
+    x, c = x.to(cuda), c.to(cuda)
+    y = gen(x, c).clone()
+    assert torch.isfinite(y).all()
+    assert torch.equal(gen(x, c), y)                               # deterministic
+    y1 = gen(x[7:8].contiguous(), c[7:8].contiguous())             # utterance 7 alone == inside the batch, bit for bit
+    assert torch.equal(y1[0], y[7])
+    with torch.no_grad():
+        r = opwg.generator_forward(folded, x[:1, :, :24000].cpu().contiguous(), c[:1, :, :84].cpu().contiguous())
+    # the first 80 frames minus the receptive field (3069 samples + upsampling halo) are independent of the truncation
+    n = 24000 - 3069 - 600
+    assert rel_err(y[0, :, :n], r[0, :, :n]) < TOL
+
+
+def test_fs2_golden(cuda, fs2):
+    m, _ = fs2
+    g = np.load(os.path.join(GOLD, "fs2_infer_small.npz"))
+    out = m.inference(torch.from_numpy(g["text"])[0].to(cuda))
+    assert out.shape[0] == int(g["durations"].sum())               # integer durations: exact
+    assert rel_err(out, torch.from_numpy(g["after"][0])) < TOL
+    g = np.load(os.path.join(GOLD, "fs2_forward_small.npz"))
+    b = {k: torch.from_numpy(g[k]).to(cuda) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+    o = m(b["text"], b["text_lengths"], b["speech"], b["speech_lengths"], b["durations"], b["pitch"], b["energy"])
+    for name, t in zip(("before", "after", "d_outs", "p_outs", "e_outs"), o[:5]):
+        assert rel_err(t, torch.from_numpy(g[name])) < TOL, name
+
+
+def test_fs2_cfg1_and_batched_inference_vs_oracle(cuda, fs2):
+    from oracle import fastspeech2 as ofs
+    m, params = fs2
+    xs, il = ofs.synth_text(1, [100])                              # cfg1: single utterance, 100 phonemes
+    with torch.no_grad():
+        _, a_ref, d_ref, p_ref, e_ref = ofs.fs2_forward(params, None, xs, il, is_inference=True)
+    before, after, d, p, e, olens = m._forward(xs.to(cuda), il.to(cuda), is_inference=True)
+    assert torch.equal(d.cpu(), d_ref)                             # bit-exact integer durations
+    assert int(olens[0]) == a_ref.shape[1]
+    assert rel_err(after, a_ref) < TOL and rel_err(p, p_ref) < TOL and rel_err(e, e_ref) < TOL
+    # speed control (alpha != 1): durations re-rounded half away from zero
+    with torch.no_grad():
+        _, a2, d2, _, _ = ofs.fs2_forward(params, None, xs, il, is_inference=True, alpha=1.3)
+    out = m.inference(xs[0].to(cuda), alpha=1.3)
+    assert out.shape[0] == a2.shape[1] and rel_err(out, a2[0]) < TOL
+    # ragged batch: every utterance identical to decoding it alone
+    lengths = [60, 100, 83, 140]
+    xs, il = ofs.synth_text(7, lengths)
+    mel, olens, _ = m.batch_inference(xs.to(cuda), il.to(cuda))
+    for i, n in enumerate(lengths):
+        with torch.no_grad():
+            r = ofs.fs2_inference(params, None, xs[i, :n])
+        L = int(olens[i])
+        assert L == r.shape[0]
+        assert rel_err(mel[i, :L], r) < TOL
+        assert L == mel.shape[1] or mel[i, L:].abs().max().item() == 0
+
+
+def test_fs2_full_batch_properties(cuda, fs2):
+    """cfg3-sized FS2 (32 utterances, T ~ U{60..140}): batch independence without the oracle."""
+    from oracle import fastspeech2 as ofs
+    m, _ = fs2
+    g = torch.Generator().manual_seed(3)
+    lengths = torch.randint(60, 141, (32,), generator=g).tolist()
+    xs, il = ofs.synth_text(3, lengths)
+    mel, olens, d = m.batch_inference(xs.to(cuda), il.to(cuda))
+    assert torch.isfinite(mel).all() and (d >= 0).all()
+    assert olens.cpu().tolist() == d.sum(1).to(torch.int64).cpu().tolist()
+    for i in (0, 13, 31):
+        single = m.inference(xs[i, :lengths[i]].to(cuda))
+        assert single.shape[0] == int(olens[i])
+        assert rel_err(mel[i, :single.shape[0]], single) < 1e-5
+
+
+def test_zscore_and_inference_wrappers(cuda, fs2, pwg):
+    from parakeet_b200.models import FastSpeech2Inference, PWGInference
+    from parakeet_b200.modules.normalizer import ZScore
+    m, _ = fs2
+    gen, _ = pwg
+    mu, sigma = torch.randn(80), torch.rand(80) + 0.5
+    norm = ZScore(mu, sigma, device=cuda)
+    text = torch.randint(1, 79, (20,)).to(cuda)
+    mel_n = m.inference(text)
+    logmel = FastSpeech2Inference(norm, m)(text)
+    assert rel_err(logmel, mel_n.cpu() * sigma + mu) < 1e-6
+    noise = torch.randn(1, 1, logmel.shape[0] * 300, device=cuda)
+    wav = PWGInference(norm, gen)(logmel, x=noise)
+    assert list(wav.shape) == [logmel.shape[0] * 300, 1] and torch.isfinite(wav).all()
+    assert rel_err(wav, gen.inference(mel_n, x=noise)) < 1e-4

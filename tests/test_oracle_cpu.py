@@ -1,0 +1,128 @@
+"""CPU tests: the oracle against its golden vectors and against independent cross-checks."""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import fastspeech2 as ofs
+from oracle import pwg as opwg
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_paddle_round_is_half_away_from_zero():
+    x = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 2.4999, 3.0])
+    assert ofs.paddle_round(x).tolist() == [1.0, 2.0, 3.0, -1.0, -2.0, 2.0, 3.0]
+    assert torch.round(x).tolist()[:3] == [0.0, 2.0, 2.0]  # torch rounds half to even: the hazard this guards against
+
+
+def test_length_regulator_reference_case_and_gather_equivalence():
+    # tests/unit/test_expansion.py:20-24 of the reference pins only the shape [2, 8, 3]
+    g = np.load(os.path.join(GOLD, "length_regulator.npz"))
+    enc, dur = torch.from_numpy(g["enc"]), torch.from_numpy(g["dur"])
+    out = ofs.length_regulator_expand(enc, dur)
+    assert list(out.shape) == [2, 8, 3]
+    assert torch.equal(out, torch.from_numpy(g["out"]))
+    # the 0/1-matrix matmul is bit-identical to a gather (what the CUDA kernel does)
+    torch.manual_seed(0)
+    x = torch.randn(4, 100, 384)
+    d = torch.randint(0, 13, (4, 100))
+    ref = ofs.length_regulator_expand(x, d)
+    for b in range(4):
+        idx = torch.repeat_interleave(torch.arange(100), d[b])
+        assert torch.equal(ref[b, :idx.numel()], x[b, idx])
+        assert ref[b, idx.numel():].abs().max() == 0 if idx.numel() < ref.shape[1] else True
+
+
+def test_attention_matches_torch_sdpa():
+    torch.manual_seed(1)
+    p = {}
+    for nm in ("linear_q", "linear_k", "linear_v", "linear_out"):
+        p[f"a.{nm}.weight"] = torch.randn(64, 64) / 8
+        p[f"a.{nm}.bias"] = torch.randn(64) * 0.1
+    x = torch.randn(3, 17, 64)
+    lens = [17, 9, 13]
+    mask = ofs.make_non_pad_mask(lens, 17).unsqueeze(-2)
+    out = ofs.attention(p, "a.", x, mask, n_head=4)
+    q = (x @ p["a.linear_q.weight"] + p["a.linear_q.bias"]).reshape(3, 17, 4, 16).transpose(1, 2)
+    k = (x @ p["a.linear_k.weight"] + p["a.linear_k.bias"]).reshape(3, 17, 4, 16).transpose(1, 2)
+    v = (x @ p["a.linear_v.weight"] + p["a.linear_v.bias"]).reshape(3, 17, 4, 16).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask.unsqueeze(1))
+    ref = ref.transpose(1, 2).reshape(3, 17, 64) @ p["a.linear_out.weight"] + p["a.linear_out.bias"]
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_fully_masked_attention_row_is_zero_not_nan():
+    scores = torch.randn(1, 1, 2, 3)
+    m = torch.ones(1, 1, 1, 3, dtype=torch.bool)
+    s = ofs.masked_fill(scores, m, float(np.finfo(np.float32).min))
+    attn = ofs.masked_fill(torch.softmax(s, dim=-1), m, 0.0)
+    assert torch.isfinite(attn).all() and attn.abs().max() == 0
+
+
+def test_positional_encoding_formula():
+    pe = ofs.positional_encoding(50, 8)[0]
+    for t in (0, 1, 7, 49):
+        for i in range(4):
+            div = math.exp(2 * i * -(math.log(10000.0) / 8))
+            assert abs(pe[t, 2 * i].item() - math.sin(t * div)) < 1e-5
+            assert abs(pe[t, 2 * i + 1].item() - math.cos(t * div)) < 1e-5
+
+
+def test_pwg_weight_norm_fold_and_upsample_shapes():
+    pw = opwg.synth_params(2, weight_norm=True)
+    assert pw["first_conv.weight_g"].dim() == 1  # paddle weight_g is 1-D [out] (tests/unit/test_pwg.py:131-132)
+    pf = opwg.fold_weight_norm(pw)
+    v, g = pw["conv_layers.3.conv.weight_v"], pw["conv_layers.3.conv.weight_g"]
+    ref = v * (g / v.reshape(128, -1).norm(dim=1)).reshape(-1, 1, 1)
+    assert torch.allclose(pf["conv_layers.3.conv.weight"], ref)
+    c = torch.randn(2, 80, 9 + 4)
+    up = opwg.conv_in_upsample_net(pf, c, [4, 5, 3, 5])
+    assert list(up.shape) == [2, 80, 9 * 300]
+
+
+def test_pwg_generator_reference_test_config_runs():
+    # shapes of tests/unit/test_pwg.py:120-136: layers 9, stacks 3, upsample [4,4,4,4], x [4,1,80*256], c [4,80,84]
+    cfg = dict(layers=9, stacks=3, upsample_scales=[4, 4, 4, 4])
+    p = opwg.synth_params(3, cfg)
+    x, c = torch.randn(1, 1, 8 * 256), torch.randn(1, 80, 8 + 4)
+    with torch.no_grad():
+        y = opwg.generator_forward(p, x, c, cfg)
+    assert list(y.shape) == [1, 1, 8 * 256] and torch.isfinite(y).all()
+
+
+def test_oracle_matches_golden_pwg():
+    g = np.load(os.path.join(GOLD, "pwg_small.npz"))
+    params = opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True))
+    with torch.no_grad():
+        y, inter = opwg.generator_forward(params, torch.from_numpy(g["x"]), torch.from_numpy(g["c"]), return_intermediates=True)
+    assert np.abs(y.numpy() - g["y"]).max() <= 1e-5 * np.abs(g["y"]).max()
+    assert abs(inter["skips"].double().sum().item() - float(g["skips_checksum"])) < 1e-2
+
+
+def test_oracle_matches_golden_fs2():
+    fp = ofs.synth_params(1)
+    g = np.load(os.path.join(GOLD, "fs2_infer_small.npz"))
+    with torch.no_grad():
+        out = ofs.fs2_inference(fp, None, torch.from_numpy(g["text"])[0])
+    assert out.shape[0] == int(g["durations"].sum())
+    assert np.abs(out.numpy() - g["after"][0]).max() <= 2e-5 * np.abs(g["after"]).max()
+    g = np.load(os.path.join(GOLD, "fs2_forward_small.npz"))
+    b = {k: torch.from_numpy(g[k]) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+    with torch.no_grad():
+        ref = ofs.fs2_forward(fp, None, b["text"], b["text_lengths"], b["speech_lengths"], b["durations"], b["pitch"], b["energy"])
+        losses = ofs.fs2_loss(ref[1], ref[0], ref[2], ref[3], ref[4], b["speech"], b["durations"], b["pitch"], b["energy"],
+                              b["text_lengths"], b["speech_lengths"])
+    assert np.abs(ref[1].numpy() - g["after"]).max() <= 2e-5 * np.abs(g["after"]).max()
+    assert np.allclose([float(v) for v in losses], g["losses"], rtol=1e-4)
+
+
+def test_fs2_padding_rows_do_not_leak_in_single_utterance_semantics():
+    # an utterance decoded alone equals itself: inference is deterministic and length = sum of rounded durations
+    fp = ofs.synth_params(1)
+    xs, il = ofs.synth_text(3, [15])
+    with torch.no_grad():
+        b, a, d, p, e = ofs.fs2_forward(fp, None, xs, il, is_inference=True)
+    assert a.shape[1] == int(d.sum()) and (d >= 0).all() and torch.equal(d, torch.round(d))
