@@ -157,6 +157,8 @@ def length_regulate(x, dur, t_out, want_f32=True, want_split=False):
     B, T, Cc = x.shape
     y = torch.empty(B, t_out, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
     ys = Split.empty((B, t_out, Cc), x.device) if want_split else None
+    if t_out == 0:   # every duration is zero: empty output, as in the reference (t_dec = 0)
+        return y, ys
     _lib.check(_lib.lib().pk_length_regulate(_ptr(x), _ptr(dur), B, T, Cc, t_out, _ptr(y),
                                              _ptr(ys.hi) if ys else None, _ptr(ys.lo) if ys else None, _stream()),
                "pk_length_regulate")
