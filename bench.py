@@ -119,7 +119,7 @@ def run_reference(args, rank):
     import torch
     from oracle import pwg as opwg
     params = opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True))
-    b_s = 2                                                   # bounded sample: 2 of the 32 utterances per step
+    b_s = 1                                                   # bounded sample: 1 of the 32 utterances per step (~5 s)
     x, c = opwg.synth_inputs(2, batch=b_s, mel_frames=FRAMES)
     cores = pick_cpu_threads(params, x, c)
     for _ in range(max(args.warmup, 1)):
