@@ -135,7 +135,7 @@ int pk_pwg_first_conv(const float* noise, const float* w, const float* bias, con
 
 /* One fused ResidualBlock.forward (:284-315) for residual = skip = 64 channels, gate = 128, kernel 3:
  *   h = conv_k3_dil(x) + b1 + conv1x1_aux(c);  z = tanh(h[:64]) * sigmoid(h[64:]);
- *   skip (+)= conv1x1_skip(z) + b_skip;  y = (conv1x1_out(z) + b_out + x) * sqrt(0.5)
+ *   skip (+)= conv1x1_skip(z)   [its bias is added once, in pk_pwg_tail];  y = (conv1x1_out(z) + b_out + x) * sqrt(0.5)
  * w1: packed [128][5*64] K-major = taps 0..2 (64 ch each) then the aux weight zero-padded to 128 channels;
  * w2: packed [128][64], rows 0..63 = conv1x1_skip, rows 64..127 = conv1x1_out; bias1 [128]; bias2 = skip bias | out bias.
  * y must not alias x.  Rows t >= lens[b] of y are written as zero and tiles wholly past lens[b] are skipped
@@ -157,15 +157,18 @@ typedef struct pk_pwg_layer_args {
   const float* bias2;
   float* skip;             /* fp32 (batch, t, 64) running sum of skips */
   int32_t skip_init;       /* 1: overwrite (first layer), 0: accumulate */
-  void* prof;              /* debug: NULL, or device uint64[40] phase-cycle counters accumulated by the kernel
+  void* prof;              /* debug: NULL, or device uint64[64] phase-cycle counters accumulated by the kernel
                               ([0..1] producer, [8..14] MMA issuer, [16..22]/[24..30] epilogue halves, [32] tiles) */
 } pk_pwg_layer_args;
 int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
 
-/* last_conv_layers (:429-440) on the scaled skip sum (:469-471): out[row] = w2 . relu(W1 relu(skip[row] * scale) + b1) + b2
- * with skip fp32 (rows, 64), W1 [64 out][64 in], w2 [64]; out fp32 (rows). */
-int pk_pwg_tail(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float scale,
-                int64_t rows, float* out, pk_stream_t stream);
+/* last_conv_layers (:429-440) on the scaled skip sum (:469-471):
+ *   out[row] = w2 . relu(W1 relu((skip[row] + skip_bias) * scale) + b1) + b2
+ * with skip fp32 (rows, 64), W1 [64 out][64 in], w2 [64]; out fp32 (rows).  skip_bias [64] (or NULL) is the sum of the
+ * layers' conv1x1_skip biases: pk_pwg_residual_layer accumulates the skip branch WITHOUT its bias (bias2[0..63] is
+ * ignored there) and the constant vector is added once here. */
+int pk_pwg_tail(const float* skip, const float* skip_bias, const float* w1, const float* b1, const float* w2, const float* b2,
+                float scale, int64_t rows, float* out, pk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * FastSpeech2 row-wise kernels (reference: parakeet/models/fastspeech2/fastspeech2.py and parakeet/modules/*).

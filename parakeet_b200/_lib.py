@@ -68,7 +68,7 @@ def _declare(L):
         "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
         "pk_pwg_first_conv": [vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
-        "pk_pwg_tail": [vp, vp, vp, vp, vp, f32, i64, vp, vp],
+        "pk_pwg_tail": [vp, vp, vp, vp, vp, vp, f32, i64, vp, vp],
         "pk_embed_pe": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],
         "pk_masked_softmax": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],

@@ -172,9 +172,15 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __
 // integer arithmetic, after which the compiler can no longer prove a pointer is in shared space and would emit
 // generic LD/ST (long-scoreboard latency); these helpers keep the accesses on the LDS/STS path.
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {   // ordered w.r.t. the other volatile smem helpers
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// read-only data written once before a __syncthreads (biases): the compiler may hoist / reorder these freely
+__device__ __forceinline__ float4 lds_const_f4(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -183,10 +189,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");

@@ -22,16 +22,26 @@ namespace pk {
 // ---------------------------------------------------------------------------------------------------------------
 // fused residual layer
 // ---------------------------------------------------------------------------------------------------------------
+// Warp roles (18 warps, 1 CTA per SM, persistent over 128-sample tiles):
+//   warp 0      TMA producer   : per tile 5 K-chunks for GEMM1 (3 dilated taps of x, 2 chunks of c; A and B = 64 KB
+//                                per stage) + 1 chunk for GEMM2 (W2 only; the A half of that stage receives z)
+//   warp 1      MMA issuer     : G1(0); then per tile { G1(i+1); G2(i) } so GEMM1 of the next tile overlaps the gate
+//   warps 2-9   gate  warps    : acc1 (TMEM) -> tanh * sigmoid -> split-bf16 z tile written (128B-swizzled) into the
+//                                A half of the pipeline stage reserved for GEMM2
+//   warps 10-17 store warps    : acc2 (TMEM) -> + bias -> per-warp 32x32 transpose in smem -> coalesced
+//                                red.global.add (skip sum) / residual + split planes (x_out)
+// TMEM: acc1[2] at columns 0/128, acc2[2] at 256/384 (fp32 128x128 each).
 constexpr int kPwgR = 64;        // residual channels
 constexpr int kPwgG = 128;       // gate channels
 constexpr int kPwgS = 64;        // skip channels
 constexpr int kPwgStages = 3;
 constexpr int kPwgTile = 128 * kSwizzleBytes;                 // 16 KB: one plane of a 128-row K-chunk
 constexpr int kPwgStageBytes = 4 * kPwgTile;                  // A hi, A lo, B hi, B lo
-constexpr int kPwgZBytes = 2 * kPwgTile;                      // z hi, z lo
-constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgZBytes + 1024 + 256 + 1024;  // + biases
-constexpr int kPwgEpiWarps = 8;
-constexpr int kPwgThreads = 64 + kPwgEpiWarps * 32;           // 320
+constexpr int kPwgStageSmem = 8 * 32 * kSwizzleBytes;         // 8 store warps x (32 rows x 128 B) transpose slices
+constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgStageSmem + 1024 + 256 + 1024;  // + align + barriers + biases
+constexpr int kPwgGateWarps = 8;
+constexpr int kPwgStoreWarps = 8;
+constexpr int kPwgThreads = 64 + (kPwgGateWarps + kPwgStoreWarps) * 32;   // 576
 constexpr int kPwgG1Chunks = 5;                               // 3 taps + 2 aux chunks (64 + 16 channels)
 
 struct PwgLayerArgs {
@@ -51,13 +61,13 @@ struct PwgLayerArgs {
 
 // phase timing (only when p.prof != NULL): accumulate clock64() deltas per section
 #define PK_TICK(k)                                      \
-  if (p.prof) {                                         \
+  if (kProf) {                                          \
     const long long n_ = clock64();                     \
     tacc[k] += n_ - tlast;                              \
     tlast = n_;                                         \
   }
 #define PK_TICK_FLUSH(base, n)                                                              \
-  if (p.prof) {                                                                             \
+  if (kProf) {                                                                              \
     for (int k_ = 0; k_ < (n); ++k_) atomicAdd(p.prof + (base) + k_, static_cast<unsigned long long>(tacc[k_])); \
   }
 
@@ -79,9 +89,17 @@ struct PwgTileIter {
   }
 };
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return __fdividef(2.f, 1.f + __expf(-2.f * v)) - 1.f; }
+// split two fp32 values into packed bf16x2 hi / lo words (cvt.rn.bf16x2.f32: one instruction per pair)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
+template <bool kProf>
 __global__ void __launch_bounds__(kPwgThreads, 1)
 pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                  const __grid_constant__ CUtensorMap tm_c_hi, const __grid_constant__ CUtensorMap tm_c_lo,
@@ -91,8 +109,8 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   // all shared-memory accesses go through 32-bit shared-space addresses (see pk_sm100.cuh)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // 1024-B aligned for SWIZZLE_128B
-  const uint32_t z_smem = smem + kPwgStages * kPwgStageBytes;
-  const uint32_t bars = z_smem + kPwgZBytes;
+  const uint32_t xpose = smem + kPwgStages * kPwgStageBytes;        // store-warp transpose slices
+  const uint32_t bars = xpose + kPwgStageSmem;
   const uint32_t full_bar = bars;                       // [stages]
   const uint32_t empty_bar = full_bar + 8 * kPwgStages; // [stages]
   const uint32_t acc1_full = empty_bar + 8 * kPwgStages;  // [2]
@@ -100,29 +118,35 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
   const uint32_t acc2_full = acc1_empty + 16;           // [2]
   const uint32_t acc2_empty = acc2_full + 16;           // [2]
   const uint32_t z_full = acc2_empty + 16;              // [1]
-  const uint32_t z_empty = z_full + 8;                  // [1]
-  const uint32_t tmem_slot = z_empty + 8;
-  const uint32_t s_bias = z_smem + kPwgZBytes + 256;    // float[256]: bias1 | bias2
+  const uint32_t g2_free = z_full + 8;                 // [1] producer -> gate warps: the GEMM2 stage of tile i may be written
+  const uint32_t tmem_slot = g2_free + 8;
+  // gate constants: [0,64) -2*log2e*bias_a, [64,128) -log2e*bias_g; store biases: [128,256) bias2
+  const uint32_t s_bias = bars + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_c_hi); tma_prefetch_desc(&tm_c_lo);
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w1_lo); tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo);
     for (int s = 0; s < kPwgStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, kPwgEpiWarps * 32);
-      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, kPwgEpiWarps * 32);
+      mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, kPwgGateWarps * 32);
+      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, kPwgStoreWarps * 32);
     }
-    mbar_init_a(z_full, kPwgEpiWarps * 32);
-    mbar_init_a(z_empty, 1);
+    mbar_init_a(z_full, kPwgGateWarps * 32);
+    mbar_init_a(g2_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_a<512>(tmem_slot);
-  if (threadIdx.x >= 64) {
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
     const int i = threadIdx.x - 64;
-    sts_f32(s_bias + 4 * i, i < 128 ? p.bias1[i] : p.bias2[i - 128]);
+    float v;
+    if (i < 64) v = -2.f * kLog2e * p.bias1[i];
+    else if (i < 128) v = -kLog2e * p.bias1[i];
+    else v = p.bias2[i - 128];
+    sts_f32(s_bias + 4 * i, v);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -162,6 +186,7 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
         mbar_wait_a(empty_bar + 8 * s, ((it / kPwgStages) & 1) ^ 1);
         PK_TICK(0)
         const uint32_t st = smem + s * kPwgStageBytes;
+        mbar_arrive_a(g2_free);     // one completion per tile: the gate warps may now write z into this stage's A half
         mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kPwgTile);
         tma_load_3d_a(st + 2 * kPwgTile, &tm_w2_hi, full_bar + 8 * s, 0, 0, 0);
         tma_load_3d_a(st + 3 * kPwgTile, &tm_w2_lo, full_bar + 8 * s, 0, 0, 0);
@@ -188,7 +213,9 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       uint32_t it = 0;
       long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tlast = clock64();
-      auto mma_chunk = [&](uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int ksteps, bool first) {
+      auto mma_chunk = [&](uint32_t d_tmem, uint32_t st, int ksteps, bool first) {
+        const uint64_t a_hi = make_smem_desc_sw128(st), a_lo = make_smem_desc_sw128(st + kPwgTile);
+        const uint64_t b_hi = make_smem_desc_sw128(st + 2 * kPwgTile), b_lo = make_smem_desc_sw128(st + 3 * kPwgTile);
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
           umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, !(first && k == 0));
@@ -209,37 +236,30 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
           mbar_wait_a(full_bar + 8 * s, (it / kPwgStages) & 1);
           PK_TICK(1)
           tcgen05_fence_after();
-          const uint32_t st = smem + s * kPwgStageBytes;
-          mma_chunk(d, make_smem_desc_sw128(st), make_smem_desc_sw128(st + kPwgTile), make_smem_desc_sw128(st + 2 * kPwgTile),
-                    make_smem_desc_sw128(st + 3 * kPwgTile), j == kPwgG1Chunks - 1 ? aux_tail_ksteps : 4, j == 0);
+          mma_chunk(d, smem + s * kPwgStageBytes, j == kPwgG1Chunks - 1 ? aux_tail_ksteps : 4, j == 0);
           umma_commit_a(empty_bar + 8 * s);
         }
         umma_commit_a(acc1_full + 8 * buf);
       };
       auto g2 = [&](int i) {
         const int buf = i & 1;
+        const int s = it % kPwgStages;
         PK_TICK(2)
-        mbar_wait_a(z_full, i & 1);
+        mbar_wait_a(z_full, i & 1);                       // gate warps wrote z into the A half of stage s
         PK_TICK(3)
         mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
         PK_TICK(4)
-        const int s = it % kPwgStages;
         mbar_wait_a(full_bar + 8 * s, (it / kPwgStages) & 1);
         PK_TICK(5)
         tcgen05_fence_after();
-        const uint32_t st = smem + s * kPwgStageBytes;
-        const uint32_t zs = z_smem;
-        mma_chunk(tmem_base + 256 + buf * 128, make_smem_desc_sw128(zs), make_smem_desc_sw128(zs + kPwgTile),
-                  make_smem_desc_sw128(st + 2 * kPwgTile), make_smem_desc_sw128(st + 3 * kPwgTile), 4, true);
+        mma_chunk(tmem_base + 256 + buf * 128, smem + s * kPwgStageBytes, 4, true);
         umma_commit_a(empty_bar + 8 * s);
-        umma_commit_a(z_empty);
         umma_commit_a(acc2_full + 8 * buf);
         ++it;
       };
       PwgTileIter ti(p);
       int b, m0;
-      int n_issued = 0;   // tiles whose GEMM1 has been issued
-      int n_done = 0;     // tiles whose GEMM2 has been issued
+      int n_issued = 0, n_done = 0;
       bool have = ti.next(b, m0);
       if (have) g1(n_issued++);
       while (have) {
@@ -250,49 +270,26 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       }
       PK_TICK(6)
       PK_TICK_FLUSH(8, 7)
-      if (p.prof) atomicAdd(p.prof + 32, static_cast<unsigned long long>(n_done));
+      if (kProf) atomicAdd(p.prof + 32, static_cast<unsigned long long>(n_done));
     }
-  } else {
-    // ------------------------------ epilogue warps ------------------------------
-    const int ew = warp - 2;
-    const int quarter = warp & 3;     // TMEM lane quarter accessible to this warp
-    const int half = ew >> 2;         // which half of the columns this warp handles
-    const int r = quarter * 32 + lane;  // row inside the tile
+  } else if (warp < 2 + kPwgGateWarps) {
+    // ------------------------------ gate warps ------------------------------
+    const int quarter = warp & 3;                 // TMEM lane quarter accessible to this warp
+    const int half = (warp - 2) >> 2;             // z columns [32*half, 32*half + 32)
+    const int r = quarter * 32 + lane;            // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const float kSqrtHalf = 0.70710678118654752440f;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
+    uint32_t it = kPwgG1Chunks;                   // mirrors the producer's stage counter: G1(0) used stages 0..4
     PwgTileIter ti(p);
-    int b, m0;
-    for (int i = 0; ti.next(b, m0); ++i) {
+    int b, m0, nb, nm0;
+    bool have = ti.next(b, m0);
+    for (int i = 0; have; ++i) {
+      const bool have_next = ti.next(nb, nm0);
+      if (have_next) it += kPwgG1Chunks;          // G1(i+1) is loaded before the GEMM2 chunk of tile i
+      const uint32_t st2 = smem + (it % kPwgStages) * kPwgStageBytes;
+      ++it;
       const int buf = i & 1;
-      const int t = m0 + r;
-      const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
-      // ---- prefetch E2's global operands (coalesced, in the transposed mapping used by the store phase) ----
-      const int c8 = lane & 7;              // 16-byte chunk (4 fp32 columns) handled in the transposed phase
-      const int rsub = lane >> 3;           // row within a group of 4
-      const int row_base = m0 + quarter * 32;
-      uint4 pre[16];                        // half 0: old skip (float4) [pass][k]; half 1: {x_hi.xy, x_lo.xy} [pass][k]
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int tt = row_base + 4 * k + rsub;
-          const long long off = (static_cast<long long>(b) * p.t + tt) * 64 + pass * 32 + 4 * c8;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (tt < p.t) {
-            if (half == 0) {
-              if (!p.skip_init) v = *reinterpret_cast<const uint4*>(p.skip + off);
-            } else {
-              const uint2 xh = __ldg(reinterpret_cast<const uint2*>(p.x_hi + off));
-              const uint2 xl = __ldg(reinterpret_cast<const uint2*>(p.x_lo + off));
-              v = make_uint4(xh.x, xh.y, xl.x, xl.y);
-            }
-          }
-          pre[pass * 8 + k] = v;
-        }
-      }
-      // ---- E1: gate ----
       PK_TICK(6)
       mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
       PK_TICK(0)
@@ -304,94 +301,136 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive_a(acc1_empty + 8 * buf);
+      // z = tanh(a + ba) * sigmoid(g + bg) = (1 - e1) / ((1 + e1)(1 + e2)), e1 = exp(-2(a+ba)), e2 = exp(-(g+bg))
+      // (one reciprocal; the exp2 argument of e1 is clamped at 60 so that the product cannot overflow where z != 0)
+      uint32_t zh[16], zl[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 ba = lds_f4(s_bias + 4 * (half * 32 + j));
-        const float4 bg = lds_f4(s_bias + 4 * (64 + half * 32 + j));
-        va[j + 0] = fast_tanh(va[j + 0] + ba.x) * fast_sigmoid(vb[j + 0] + bg.x);
-        va[j + 1] = fast_tanh(va[j + 1] + ba.y) * fast_sigmoid(vb[j + 1] + bg.y);
-        va[j + 2] = fast_tanh(va[j + 2] + ba.z) * fast_sigmoid(vb[j + 2] + bg.z);
-        va[j + 3] = fast_tanh(va[j + 3] + ba.w) * fast_sigmoid(vb[j + 3] + bg.w);
+        const float4 ca = lds_const_f4(s_bias + 4 * (half * 32 + j));
+        const float4 cg = lds_const_f4(s_bias + 4 * (64 + half * 32 + j));
+        const float cav[4] = {ca.x, ca.y, ca.z, ca.w};
+        const float cgv[4] = {cg.x, cg.y, cg.z, cg.w};
+        float z[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float e1 = exp2f(fminf(fmaf(va[j + e], -2.f * kLog2e, cav[e]), 60.f));
+          const float e2 = exp2f(fmaf(vb[j + e], -kLog2e, cgv[e]));
+          const float den = fmaf(e1, e2, e1 + e2) + 1.f;
+          z[e] = __fdividef(1.f - e1, den);
+        }
+        split2(z[0], z[1], zh[j / 2], zl[j / 2]);
+        split2(z[2], z[3], zh[j / 2 + 1], zl[j / 2 + 1]);
       }
       PK_TICK(1)
-      mbar_wait_a(z_empty, (i & 1) ^ 1);  // GEMM2 of the previous tile has finished reading z
+      // The GEMM2 stage of this tile is ours once the producer has claimed it (it waited for the MMA to release it).
+      // g2_free completes exactly once per tile and cannot run more than one tile ahead of this wait (the next claim
+      // needs GEMM2 of this tile, which needs our z), so the parity wait cannot alias.
+      mbar_wait_a(g2_free, i & 1);
       PK_TICK(2)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 h, l;
-        split8(va + 8 * q, h, l);
         const int chunk = (half * 4 + q) ^ (r & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-        sts_u4(z_smem + r * kSwizzleBytes + chunk * 16, h);
-        sts_u4(z_smem + kPwgTile + r * kSwizzleBytes + chunk * 16, l);
+        sts_u4(st2 + r * kSwizzleBytes + chunk * 16, make_uint4(zh[4 * q], zh[4 * q + 1], zh[4 * q + 2], zh[4 * q + 3]));
+        sts_u4(st2 + kPwgTile + r * kSwizzleBytes + chunk * 16, make_uint4(zl[4 * q], zl[4 * q + 1], zl[4 * q + 2], zl[4 * q + 3]));
       }
       fence_proxy_async_smem();
       mbar_arrive_a(z_full);
-      // ---- E2: skip / residual ----
       PK_TICK(3)
-      mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
-      PK_TICK(4)
-      tcgen05_fence_after();
-      float v0[32], v1[32];
-      __syncwarp();
-      tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64, v0);
-      tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64 + 32, v1);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive_a(acc2_empty + 8 * buf);
-      // Transpose through shared memory so that global traffic is coalesced: each warp stages 32 rows x 32 fp32
-      // columns in a private 4 KB slice of the (now idle) z buffer - quarter q owns rows 32q..32q+31 of both z planes,
-      // its two warps take one plane each - then re-reads it with 8 lanes per row (4 rows x 128 B per instruction).
-      {
-        const uint32_t slice = z_smem + half * kPwgTile + quarter * 32 * kSwizzleBytes;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const float* v = pass == 0 ? v0 : v1;
-          const uint32_t bias = s_bias + 4 * (128 + half * 64 + pass * 32);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 bb = lds_f4(bias + 16 * c);
-            sts_f4(slice + lane * kSwizzleBytes + ((c ^ (lane & 7)) << 4),
-                   make_float4(v[4 * c] + bb.x, v[4 * c + 1] + bb.y, v[4 * c + 2] + bb.z, v[4 * c + 3] + bb.w));
-          }
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rl = 4 * k + rsub;
-            const int tt = row_base + rl;
-            const float4 o = lds_f4(slice + rl * kSwizzleBytes + ((c8 ^ (rl & 7)) << 4));
-            if (tt < p.t) {
-              const long long off = (static_cast<long long>(b) * p.t + tt) * 64 + pass * 32 + 4 * c8;
-              if (half == 0) {
-                const uint4 old = pre[pass * 8 + k];   // zeros when skip_init
-                *reinterpret_cast<float4*>(p.skip + off) =
-                    make_float4(o.x + __uint_as_float(old.x), o.y + __uint_as_float(old.y), o.z + __uint_as_float(old.z),
-                                o.w + __uint_as_float(old.w));
-              } else {
-                const uint2 xh = make_uint2(pre[pass * 8 + k].x, pre[pass * 8 + k].y);
-                const uint2 xl = make_uint2(pre[pass * 8 + k].z, pre[pass * 8 + k].w);
-                const bool live = tt < len;
-                float y[4];
-                y[0] = (o.x + bf16_bits_to_float(xh.x & 0xffffu) + bf16_bits_to_float(xl.x & 0xffffu)) * kSqrtHalf;
-                y[1] = (o.y + bf16_bits_to_float(xh.x >> 16) + bf16_bits_to_float(xl.x >> 16)) * kSqrtHalf;
-                y[2] = (o.z + bf16_bits_to_float(xh.y & 0xffffu) + bf16_bits_to_float(xl.y & 0xffffu)) * kSqrtHalf;
-                y[3] = (o.w + bf16_bits_to_float(xh.y >> 16) + bf16_bits_to_float(xl.y >> 16)) * kSqrtHalf;
-                __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split_bf16(live ? y[e] : 0.f, h[e], l[e]);
-                *reinterpret_cast<uint2*>(p.y_hi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                *reinterpret_cast<uint2*>(p.y_lo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
-              }
-            }
-          }
-          __syncwarp();
-        }
-        // both warps of this quarter must be done with their slices before either writes the next z tile into them
-        PK_TICK(5)
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      }
+      have = have_next; b = nb; m0 = nm0;
     }
     PK_TICK(6)
     if (lane == 0 && quarter == 0) { PK_TICK_FLUSH(16 + half * 8, 7) }
+  } else {
+    // ------------------------------ store warps ------------------------------
+    const int sw = warp - 2 - kPwgGateWarps;      // 0..7
+    const int quarter = warp & 3;
+    const int half = sw >> 2;                     // 0: skip columns (acc2 cols 0..63), 1: out columns (64..127)
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t slice = xpose + sw * (32 * kSwizzleBytes);
+    const int c8 = lane & 7;                      // 16-byte chunk (4 fp32 columns) handled in the transposed phase
+    const int rsub = lane >> 3;                   // row within a group of 4
+    const float kSqrtHalf = 0.70710678118654752440f;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+    PwgTileIter ti(p);
+    int b, m0;
+    for (int i = 0; ti.next(b, m0); ++i) {
+      const int buf = i & 1;
+      const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
+      const int row_base = m0 + quarter * 32;
+      // prefetch the residual input x for the out half: this thread's row, 64 channels of both planes (8 + 8 x 16 B)
+      uint4 pre[16];
+      const int trow = row_base + lane;
+      const long long row_off = (static_cast<long long>(b) * p.t + trow) * 64;
+      if (half == 1 && trow < p.t) {
+        const uint4* xh = reinterpret_cast<const uint4*>(p.x_hi + row_off);
+        const uint4* xl = reinterpret_cast<const uint4*>(p.x_lo + row_off);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { pre[q] = __ldg(xh + q); pre[8 + q] = __ldg(xl + q); }
+      }
+      PK_TICK(6)
+      mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
+      PK_TICK(0)
+      tcgen05_fence_after();
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64 + pass * 32, v);
+        tmem_ld_wait();
+        PK_TICK(2)
+        if (pass == 1) {
+          tcgen05_fence_before();
+          mbar_arrive_a(acc2_empty + 8 * buf);
+        }
+        if (half == 0) {
+          const int tt = row_base + lane;
+          if (tt < p.t) {
+            float* dst = p.skip + (static_cast<long long>(b) * p.t + tt) * 64 + pass * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (p.skip_init) {
+                *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                             "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+              }
+            }
+          }
+          PK_TICK(5)
+          continue;
+        }
+        const uint32_t bias = s_bias + 4 * (128 + 64 + pass * 32);   // b_out (the skip biases are summed into the tail)
+        if (trow < p.t) {
+          const bool live = trow < len;
+          uint4* yh = reinterpret_cast<uint4*>(p.y_hi + row_off + pass * 32);
+          uint4* yl = reinterpret_cast<uint4*>(p.y_lo + row_off + pass * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                 // 8 channels per iteration
+            const float4 b0 = lds_const_f4(bias + 32 * q), b1 = lds_const_f4(bias + 32 * q + 16);
+            const float bo[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const uint4 h4 = pre[pass * 4 + q], l4 = pre[8 + pass * 4 + q];
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+            const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+              const float x1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              const float y0 = live ? (v[8 * q + 2 * e] + bo[2 * e] + x0) * kSqrtHalf : 0.f;
+              const float y1 = live ? (v[8 * q + 2 * e + 1] + bo[2 * e + 1] + x1) * kSqrtHalf : 0.f;
+              split2(y0, y1, oh[e], ol[e]);
+            }
+            yh[q] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            yl[q] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+          }
+        }
+        PK_TICK(5)
+      }
+      PK_TICK(1)
+    }
+    PK_TICK(6)
+    if (lane == 0 && quarter == 0) { PK_TICK_FLUSH(40 + half * 8, 7) }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -546,13 +585,18 @@ __global__ void pwg_first_conv_kernel(const float* __restrict__ noise, const flo
 
 // tail: y = W2 relu(W1 relu(skips * scale) + b1) + b2, skip channels = 64, out channels = 1
 __global__ void __launch_bounds__(256)
-pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ w1 /*[64][64] out,in*/, const float* __restrict__ b1,
+pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ skip_bias /*[64] or NULL*/,
+                const float* __restrict__ w1 /*[64][64] out,in*/, const float* __restrict__ b1,
                 const float* __restrict__ w2 /*[64]*/, const float* __restrict__ b2, float scale, long long rows,
                 float* __restrict__ out) {
   __shared__ float4 sw1[64 * 16];
-  __shared__ float sb1[64], sw2[64];
+  __shared__ float sb1[64], sw2[64], ssb[64];
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw1[i] = reinterpret_cast<const float4*>(w1)[i];
-  if (threadIdx.x < 64) { sb1[threadIdx.x] = b1[threadIdx.x]; sw2[threadIdx.x] = w2[threadIdx.x]; }
+  if (threadIdx.x < 64) {
+    sb1[threadIdx.x] = b1[threadIdx.x];
+    sw2[threadIdx.x] = w2[threadIdx.x];
+    ssb[threadIdx.x] = skip_bias ? skip_bias[threadIdx.x] : 0.f;
+  }
   __syncthreads();
   const float bias2 = __ldg(b2);
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < rows;
@@ -562,8 +606,8 @@ pwg_tail_kernel(const float* __restrict__ skip, const float* __restrict__ w1 /*[
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const float4 v = __ldg(sp + q);
-      s[4 * q] = fmaxf(v.x * scale, 0.f); s[4 * q + 1] = fmaxf(v.y * scale, 0.f);
-      s[4 * q + 2] = fmaxf(v.z * scale, 0.f); s[4 * q + 3] = fmaxf(v.w * scale, 0.f);
+      s[4 * q] = fmaxf((v.x + ssb[4 * q]) * scale, 0.f); s[4 * q + 1] = fmaxf((v.y + ssb[4 * q + 1]) * scale, 0.f);
+      s[4 * q + 2] = fmaxf((v.z + ssb[4 * q + 2]) * scale, 0.f); s[4 * q + 3] = fmaxf((v.w + ssb[4 * q + 3]) * scale, 0.f);
     }
     float y = bias2;
 #pragma unroll 2
@@ -611,7 +655,8 @@ extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t str
   if ((rc = encode_tmap_bf16_3d(&tw2_lo, a->w2_lo, 64, 128, 1, 64, 0, 128))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwgSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwgSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwgSmem));
     attr_set = true;
   }
   PwgLayerArgs p;
@@ -623,8 +668,12 @@ extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t str
   p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
   p.prof = static_cast<unsigned long long*>(a->prof);
   const int grid = std::min(p.total_tiles, sm_count());
-  pwg_layer_kernel<<<grid, kPwgThreads, kPwgSmem, static_cast<cudaStream_t>(stream)>>>(tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi, tw1_lo,
-                                                                                        tw2_hi, tw2_lo, p);
+  if (p.prof != nullptr)
+    pwg_layer_kernel<true><<<grid, kPwgThreads, kPwgSmem, static_cast<cudaStream_t>(stream)>>>(tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi,
+                                                                                               tw1_lo, tw2_hi, tw2_lo, p);
+  else
+    pwg_layer_kernel<false><<<grid, kPwgThreads, kPwgSmem, static_cast<cudaStream_t>(stream)>>>(tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi,
+                                                                                                tw1_lo, tw2_hi, tw2_lo, p);
   PK_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PK_OK;
@@ -690,13 +739,13 @@ extern "C" int pk_pwg_first_conv(const float* noise, const float* w, const float
   return PK_OK;
 }
 
-extern "C" int pk_pwg_tail(const float* skip, const float* w1, const float* b1, const float* w2, const float* b2, float scale,
-                           int64_t rows, float* out, pk_stream_t stream) {
+extern "C" int pk_pwg_tail(const float* skip, const float* skip_bias, const float* w1, const float* b1, const float* w2,
+                           const float* b2, float scale, int64_t rows, float* out, pk_stream_t stream) {
   PK_CHECK_ARG(skip && w1 && b1 && w2 && b2 && out, "NULL pointer");
   PK_CHECK_ARG(rows > 0, "bad sizes");
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<long long>((rows + threads - 1) / threads, pk::sm_count() * 8LL));
-  pk::pwg_tail_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(skip, w1, b1, w2, b2, scale, rows, out);
+  pk::pwg_tail_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(skip, skip_bias, w1, b1, w2, b2, scale, rows, out);
   PK_CHECK_CUDA(cudaGetLastError());
   pk::count_launch();
   return PK_OK;

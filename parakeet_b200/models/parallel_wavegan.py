@@ -173,6 +173,7 @@ class PWGGenerator(Layer):
             layers.append(dict(w1=_split_host(w1, dev), w2=_split_host(w2, dev), b1=b1.contiguous().to(dev),
                                b2=b2.contiguous().to(dev), dil=2 ** (i % (self.layers // self.stacks))))
         pk["layers"] = layers
+        pk["skip_bias_sum"] = torch.stack([p.get(f"conv_layers.{i}.conv1x1_skip.bias", zeros64) for i in range(self.layers)]).double().sum(0).float().contiguous().to(dev)
         pk["tail_w1"] = p["last_conv_layers.1.weight"][:, :, 0].contiguous().to(dev)
         pk["tail_b1"] = p["last_conv_layers.1.bias"].contiguous().to(dev)
         pk["tail_w2"] = p["last_conv_layers.3.weight"].reshape(-1).contiguous().to(dev)
@@ -248,7 +249,7 @@ class PWGGenerator(Layer):
             ev_b.record()
             ev.append((ev_a, ev_b))
         out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
-        _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
+        _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
         self._last_x = src  # layer-30 residual stream (tests)
         return out

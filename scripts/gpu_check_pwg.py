@@ -30,7 +30,7 @@ y = gen(x.to(dev), c.to(dev))
 torch.cuda.synchronize()
 print("c planes err:", err(gen._ws[(2, 12000)]["c"].float().transpose(1, 2), c_ref))
 print("x30 err:", err(gen._last_x.float().transpose(1, 2), inter["x_layers"][-1]))
-print("skip err:", err(gen._ws[(2, 12000)]["skip"].transpose(1, 2) * math.sqrt(1 / 30), inter["skips"]))
+print("skip err (incl. deferred bias):", err((gen._ws[(2, 12000)]["skip"] + gen._pack()["skip_bias_sum"]).transpose(1, 2) * math.sqrt(1 / 30), inter["skips"]))
 e = err(y, y_ref)
 print("generator out err:", e, "shape", tuple(y.shape), flush=True)
 bad = e > 1e-3
@@ -83,6 +83,6 @@ if "--time" in sys.argv:
     # check a slice against the oracle run on utterance 0 only (CPU ~1-2 s per utterance-second)
     with torch.no_grad():
         r0 = opwg.generator_forward(folded, x[:1, :, :].cpu(), c[:1].cpu())
-    print("cfg2 utt0 err:", err(y[:1], r0))
+    e = err(y[:1], r0); bad |= e > 1e-3; print("cfg2 utt0 err:", e)
 print("FAILED" if bad else "ALL OK")
 sys.exit(1 if bad else 0)

@@ -11,13 +11,14 @@ y = gen(x.cuda(), c.cuda())
 torch.cuda.synchronize()
 print(y.std().item())
 # phase timing
-gen._prof = torch.zeros(40, dtype=torch.int64, device="cuda")
+gen._prof = torch.zeros(64, dtype=torch.int64, device="cuda")
 y = gen(x.cuda(), c.cuda()); torch.cuda.synchronize()
 pr = gen._prof.cpu().tolist(); nt = max(pr[32], 1)
 names = {0: "prod wait_empty", 1: "prod issue", 8: "mma wait acc1_empty", 9: "mma wait full(G1)", 10: "mma issue", 11: "mma wait z_full",
          12: "mma wait acc2_empty", 13: "mma wait full(G2)", 14: "mma other",
-         16: "epi0 wait acc1_full", 17: "epi0 ld+gate", 18: "epi0 wait z_empty", 19: "epi0 z store", 20: "epi0 wait acc2_full", 21: "epi0 E2", 22: "epi0 barrier+loop",
-         24: "epi1 wait acc1_full", 25: "epi1 ld+gate", 26: "epi1 wait z_empty", 27: "epi1 z store", 28: "epi1 wait acc2_full", 29: "epi1 E2", 30: "epi1 barrier+loop"}
+         16: "gate0 wait acc1_full", 17: "gate0 ld+math", 18: "gate0 wait g2 stage", 19: "gate0 z store", 22: "gate0 loop",
+         40: "skip wait acc2_full", 41: "skip rest", 42: "skip tmem ld", 43: "skip sts", 44: "skip lds", 45: "skip red/st", 46: "skip loop+prefetch",
+         48: "out wait acc2_full", 49: "out rest", 50: "out tmem ld", 51: "out sts", 52: "out lds", 53: "out global", 54: "out loop+prefetch"}
 print("tiles (all CTAs, all layers):", nt)
 for k, n in names.items():
     print(f"  {n:24s} {pr[k] / nt:9.0f} cycles/tile")
