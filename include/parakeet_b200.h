@@ -211,6 +211,25 @@ int pk_variance_embed_add(const float* hs, const float* pitch, const float* ener
 int pk_zscore(const float* x, const float* mu, const float* sigma, int32_t c, int64_t n, int32_t inverse, float* y,
               pk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * STFT / mel front-end: batched radix-2 FFT (one CTA per frame, no cuFFT) with fused epilogues.
+ * Replaces STFT.forward / .power / .magnitude (parakeet/modules/audio.py:161-215: reflect pad + conv1d with the
+ * windowed DFT matrix), MelScale.forward (:218-229), stft() of modules/stft_loss.py:20-67 and the numpy/librosa
+ * feature path of data/get_feats.py:47-88 (log-mel) and :196-203 (frame energy).
+ *   x (batch, t) fp32; window (n_fft) fp32 = scipy get_window(fftbins=True) centre-padded to n_fft (host builds it);
+ *   twiddle (n_fft/2) float2 = (cos, -sin)(2 pi j / n_fft); center != 0: reflect padding n_fft/2, frames = 1 + t/hop.
+ * Outputs (any may be NULL): re / im (batch, bins, frames); mag = sqrt(max(re^2+im^2, power_clip)) (power_clip < 0:
+ * no clip) in layout 0 (batch, bins, frames) or 1 (batch, frames, bins); mel (batch, frames, n_mels) = mel_w (n_mels,
+ * bins) . mag, optionally log10(max(., mel_clip)); energy (batch, frames) = sqrt(max(sum_k |X|^2, energy_clip)).
+ * ------------------------------------------------------------------------------------------------------------ */
+int pk_stft(const float* x, int32_t batch, int32_t t, const float* window, const void* twiddle, int32_t n_fft, int32_t hop,
+            int32_t center, float* re, float* im, float* mag, int32_t mag_layout, float power_clip, const float* mel_w,
+            int32_t n_mels, float* mel, int32_t mel_log10, float mel_clip, float* energy, float energy_clip, pk_stream_t stream);
+
+/* Reductions behind SpectralConvergenceLoss / LogSTFTMagnitudeLoss (modules/stft_loss.py:70-118) on two magnitude
+ * spectrograms of n elements: out3 = { sum (y-x)^2, sum y^2, sum |log max(y,eps) - log max(x,eps)| } (device fp32[3]). */
+int pk_spectral_loss_sums(const float* x_mag, const float* y_mag, int64_t n, float eps, float* out3, pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
