@@ -118,7 +118,9 @@ class MelScale(Layer):
     def forward(self, spec):
         """(B, bins, frames) -> (B, n_mels, frames) through the tensor-core GEMM (frames as rows)."""
         from .. import ops
-        a = ops.Split.from_f32(spec.transpose(1, 2).contiguous())            # (B, frames, bins)
+        spec_t = spec.transpose(1, 2)                                          # (B, frames, bins)
+        pad = (-spec_t.shape[-1]) % 8                                          # TMA row pitch must be a multiple of 16 B
+        a = ops.Split.from_f32(torch.nn.functional.pad(spec_t, (0, pad)).contiguous())
         w = ops.pack_weight(self.weight, spec.device)
         y, _ = ops.conv_gemm(a, w, n=self.weight.shape[0], k=self.weight.shape[1])
         return y.transpose(1, 2)
