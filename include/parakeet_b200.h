@@ -230,6 +230,35 @@ int pk_stft(const float* x, int32_t batch, int32_t t, const float* window, const
  * spectrograms of n elements: out3 = { sum (y-x)^2, sum y^2, sum |log max(y,eps) - log max(x,eps)| } (device fp32[3]). */
 int pk_spectral_loss_sums(const float* x_mag, const float* y_mag, int64_t n, float eps, float* out3, pk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * WaveFlow inference (reference: parakeet/models/waveflow.py).  The per-row residual net of Flow.inverse (:515-556,
+ * ResidualBlock.add_input :248-294) runs its three GEMMs per layer through pk_conv_gemm on a channels-last row
+ * (batch, W, C): the 3-row causal buffer is a (batch, W, 3C) split-bf16 ring (slot = row mod 3) convolved along W with
+ * 3 dilated taps and K = 3C; the kernels below are the row-wise glue.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* One layer of waveflow.UpsampleNet.forward (:103-132): Conv2DTranspose(1,1,(3,2f),stride (1,f),padding (1,f/2)) over
+ * (mel, time), trim of the last f columns if trim != 0, leaky_relu(slope).  x (batch, c, t_in) -> y (batch, c,
+ * t_in*f - trim*f); w [3][2f] (Paddle [1,1,3,2f]), bias [1]. */
+int pk_waveflow_upsample(const float* x, const float* w, const float* bias, int32_t batch, int32_t c, int32_t t_in, int32_t factor,
+                         int32_t trim, float slope, float* y, pk_stream_t stream);
+/* Flow.input_proj (:437-442, 1x1 conv 1 -> C) on one row: state[b,w,:] = w * x_row[b,w] + bias (fp32 (batch, W, C)) and
+ * the same values as split planes into columns [col0, col0 + C) of a (batch, W, ld) ring buffer. */
+int pk_waveflow_input_proj(const float* x_row, int64_t x_batch_stride, const float* w, const float* bias, int32_t batch,
+                           int32_t width, int32_t c, float* state, void* buf_hi, void* buf_lo, int32_t ld, int32_t col0,
+                           pk_stream_t stream);
+/* tanh(h[:, :c]) * sigmoid(h[:, c:]) (waveflow.py:280-281, also parallel_wavegan.py:310-311): h fp32 (rows, 2c) ->
+ * split planes (rows, c). */
+int pk_gated_activation(const float* h, int64_t rows, int32_t c, void* z_hi, void* z_lo, pk_stream_t stream);
+/* res / skip update of ResidualBlock.add_input (:283-286) + ResidualNet.add_input (:385-392): o fp32 (rows, 2c);
+ * state += o[:, :c]; skip = skip_init ? o[:, c:] : skip + o[:, c:]; optional split copy of the new state into the next
+ * layer's ring buffer (columns [col0, col0 + c) of a (rows, ld) plane). */
+int pk_waveflow_layer_update(const float* o, int64_t rows, int32_t c, float* state, float* skip, int32_t skip_init, void* buf_hi,
+                             void* buf_lo, int32_t ld, int32_t col0, pk_stream_t stream);
+/* Flow._predict_row_parameters tail + _inverse_transform_row (:496-510): (logs, b) = output_proj(skip) (C -> 2, w [2][C]);
+ * x_next[b,w] = (z_row[b,w] - b) * exp(-logs). */
+int pk_waveflow_row_out(const float* skip, const float* w, const float* bias, const float* z_row, int64_t z_batch_stride,
+                        int32_t batch, int32_t width, int32_t c, float* x_next, int64_t x_batch_stride, pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

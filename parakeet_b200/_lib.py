@@ -78,6 +78,11 @@ def _declare(L):
         "pk_mask_rows": [vp, vp, i32, i32, i32, vp],
         "pk_variance_embed_add": [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp],
         "pk_zscore": [vp, vp, vp, i32, i64, i32, vp, vp],
+        "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
+        "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],
+        "pk_gated_activation": [vp, i64, i32, vp, vp, vp],
+        "pk_waveflow_layer_update": [vp, i64, i32, vp, vp, i32, vp, vp, i32, i32, vp],
+        "pk_waveflow_row_out": [vp, vp, vp, vp, i64, i32, i32, i32, vp, i64, vp],
         "pk_spectral_loss_sums": [vp, vp, i64, f32, vp, vp],
         "pk_stft": [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, i32, vp, i32, f32, vp, f32, vp],
     }

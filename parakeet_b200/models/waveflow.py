@@ -1,0 +1,190 @@
+"""ConditionalWaveFlow inference on B200 - host side (reference parakeet/models/waveflow.py:714-909).
+
+Same constructor as the reference (`upsample_factors, n_flows, n_layers, n_group, channels, n_mels, kernel_size`), same
+state-dict keys (`encoder.{i}.{weight_g,weight_v,bias}`, `decoder.{f}.input_proj.*`,
+`decoder.{f}.resnet.{l}.{conv,condition_proj,out_proj}.*`, `decoder.{f}.output_proj.{weight,bias}`), `infer(mel)` and
+`predict(mel)`.  All arithmetic is in libparakeet_b200.so; fold / permute / row slicing are torch views and gathers.
+
+Supported this round: kernel_size (3, 3) and n_group in {8, 16} (height dilation 1 -> a 3-row causal buffer), which
+covers the shipped config (examples/waveflow/config.py).  Training (`forward`, WaveFlowLoss) is not implemented.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..layer import Layer
+from ..ops import Split, _ptr, _stream
+
+
+def _fold_wn(params):
+    out = {}
+    for k, v in params.items():
+        if k.endswith("weight_g"):
+            continue
+        if k.endswith("weight_v"):
+            g = params[k[:-1] + "g"]
+            norm = v.reshape(v.shape[0], -1).norm(dim=1)
+            out[k[:-2]] = v * (g / norm).reshape([-1] + [1] * (v.dim() - 1))
+        else:
+            out[k] = v
+    return out
+
+
+class ConditionalWaveFlow(Layer):
+    def __init__(self, upsample_factors, n_flows, n_layers, n_group, channels, n_mels, kernel_size=(3, 3), device=None, seed=0):
+        super().__init__(device)
+        if isinstance(kernel_size, int):
+            kernel_size = (kernel_size, kernel_size)
+        if tuple(kernel_size) != (3, 3) or n_group not in (8, 16):
+            raise NotImplementedError("this round supports kernel_size (3,3) and n_group 8 / 16 (height dilation 1)")
+        if n_group % 2 or n_flows % 2:
+            raise ValueError("number of flows and number of group must be even")
+        if channels % 64:
+            raise NotImplementedError("channels must be a multiple of 64")
+        self.upsample_factors = list(upsample_factors)
+        self.n_flows, self.n_layers, self.n_group, self.channels, self.n_mels = n_flows, n_layers, n_group, channels, n_mels
+        g = torch.Generator().manual_seed(seed)
+
+        def u(*shape, std):
+            return (torch.rand(*shape, generator=g) * 2 - 1) * std
+
+        def wn(name, w):
+            self._register(name + ".weight_g", w.reshape(w.shape[0], -1).norm(dim=1))
+            self._register(name + ".weight_v", w)
+
+        import math
+        for i, f in enumerate(self.upsample_factors):
+            std = math.sqrt(1 / (3 * 2 * f))
+            wn(f"encoder.{i}", u(1, 1, 3, 2 * f, std=std))
+            self._register(f"encoder.{i}.bias", u(1, std=std))
+        C = channels
+        for fl in range(n_flows):
+            pre = f"decoder.{fl}."
+            wn(pre + "input_proj", u(C, 1, 1, 1, std=1.0))
+            self._register(pre + "input_proj.bias", u(C, std=1.0))
+            for l in range(n_layers):
+                q = f"{pre}resnet.{l}."
+                std = math.sqrt(1 / (C * 9))
+                wn(q + "conv", u(2 * C, C, 3, 3, std=std))
+                self._register(q + "conv.bias", u(2 * C, std=std))
+                std = math.sqrt(1 / n_mels)
+                wn(q + "condition_proj", u(2 * C, n_mels, 1, 1, std=std))
+                self._register(q + "condition_proj.bias", u(2 * C, std=std))
+                std = math.sqrt(1 / C)
+                wn(q + "out_proj", u(2 * C, C, 1, 1, std=std))
+                self._register(q + "out_proj.bias", u(2 * C, std=std))
+            self._register(pre + "output_proj.weight", torch.zeros(2, C, 1, 1))   # reference: Constant(0.)
+            self._register(pre + "output_proj.bias", torch.zeros(2))
+        idx = list(range(n_group))
+        half = n_group // 2
+        self.perms = [idx[::-1] if i < n_flows // 2 else list(reversed(idx[:half])) + list(reversed(idx[half:]))
+                      for i in range(n_flows)]                                       # waveflow.py:602-615
+
+    def _pack(self):
+        if self._packed is not None:
+            return self._packed
+        p = {k: v.detach().float().cpu() for k, v in _fold_wn(self._params).items()}
+        dev, C = self.device, self.channels
+        pk = {"enc": [(p[f"encoder.{i}.weight"].reshape(3, -1).contiguous().to(dev), p[f"encoder.{i}.bias"].to(dev))
+                      for i in range(len(self.upsample_factors))], "flows": []}
+        for fl in range(self.n_flows):
+            pre = f"decoder.{fl}."
+            layers = []
+            for l in range(self.n_layers):
+                q = f"{pre}resnet.{l}."
+                w = p[q + "conv.weight"]                                  # [2C, C, kh, kw]
+                variants = []
+                for v in range(3):                                        # row step i with i % 3 == v: slot s holds kh = (s - i) % 3
+                    wk = torch.zeros(2 * C, 3 * C, 3)
+                    for s in range(3):
+                        wk[:, s * C:(s + 1) * C, :] = w[:, :, (s - v) % 3, :]
+                    variants.append(ops.pack_weight(wk, dev))
+                layers.append(dict(conv=variants, conv_b=p[q + "conv.bias"].to(dev),
+                                   cond=ops.pack_weight(p[q + "condition_proj.weight"][:, :, 0, 0], dev),
+                                   cond_b=p[q + "condition_proj.bias"].to(dev),
+                                   out=ops.pack_weight(p[q + "out_proj.weight"][:, :, 0, 0], dev), out_b=p[q + "out_proj.bias"].to(dev)))
+            pk["flows"].append(dict(in_w=p[pre + "input_proj.weight"].reshape(-1).contiguous().to(dev),
+                                    in_b=p[pre + "input_proj.bias"].to(dev), layers=layers,
+                                    out_w=p[pre + "output_proj.weight"].reshape(2, C).contiguous().to(dev),
+                                    out_b=p[pre + "output_proj.bias"].to(dev)))
+        self._packed = pk
+        return pk
+
+    def encode(self, mel, trim_conv_artifact=True):
+        """UpsampleNet.forward (:103-132): (B, n_mels, T') -> (B, n_mels, T)."""
+        pk = self._pack()
+        x = mel.contiguous().float()
+        L = _lib.lib()
+        for (w, b), f in zip(pk["enc"], self.upsample_factors):
+            B, Cm, Tin = x.shape
+            y = torch.empty(B, Cm, Tin * f - (f if trim_conv_artifact else 0), device=x.device)
+            _lib.check(L.pk_waveflow_upsample(_ptr(x), _ptr(w), _ptr(b), B, Cm, Tin, f, 1 if trim_conv_artifact else 0, 0.4,
+                                              _ptr(y), _stream()), "pk_waveflow_upsample")
+            x = y
+        return x
+
+    def inverse(self, z, condition):
+        """WaveFlow.inverse (:674-711): z (B, T), condition (B, n_mels, T) -> audio (B, T')."""
+        pk = self._pack()
+        L = _lib.lib()
+        G, C, NL = self.n_group, self.channels, self.n_layers
+        pruned = z.shape[-1] // G * G
+        z, condition = z[:, :pruned].float(), condition[:, :, :pruned]
+        B = z.shape[0]
+        W = pruned // G
+        dev = z.device
+        z = z.reshape(B, W, G).transpose(1, 2).contiguous()                               # (B, H, W): sample t = w*G + h
+        cond = condition.reshape(B, self.n_mels, W, G).permute(0, 3, 2, 1).contiguous()   # (B, H, W, n_mels) channels-last
+        cond_s = Split.from_f32(cond)
+        cmap = list(range(G))                                                             # cumulative row permutation of the condition
+        state = torch.empty(B, W, C, device=dev)
+        skip = torch.empty(B, W, C, device=dev)
+        h = torch.empty(B, W, 2 * C, device=dev)
+        o = torch.empty(B, W, 2 * C, device=dev)
+        zt = Split.empty((B, W, C), dev)
+        bufs = [Split.zeros((B, W, 3 * C), dev) for _ in range(NL)]
+        st = _stream()
+        rows = B * W
+        for fi in reversed(range(self.n_flows)):
+            perm = self.perms[fi]
+            z = z[:, perm, :].contiguous()                                                # geo.shuffle_dim(z, 2, perm)
+            cmap = [cmap[j] for j in perm]
+            fw = pk["flows"][fi]
+            x = torch.empty_like(z)
+            x[:, 0] = z[:, 0]
+            for b_ in bufs:
+                b_.hi.zero_()
+                b_.lo.zero_()
+            for i in range(1, G):
+                slot = (i - 1) % 3                                                        # ring slot of the newest row (row i-1)
+                _lib.check(L.pk_waveflow_input_proj(_ptr(x[:, i - 1]), G * W, _ptr(fw["in_w"]), _ptr(fw["in_b"]), B, W, C,
+                                                    _ptr(state), _ptr(bufs[0].hi), _ptr(bufs[0].lo), 3 * C, slot * C, st),
+                           "pk_waveflow_input_proj")
+                c_row = Split(cond_s.hi[:, cmap[i]], cond_s.lo[:, cmap[i]])              # (B, W, n_mels) views, batch stride G*W*n_mels
+                for l, lay in enumerate(fw["layers"]):
+                    ops.conv_gemm(bufs[l], lay["conv"][i % 3], n=2 * C, k=3 * C, taps=3, dil=2 ** l, bias=lay["conv_b"], y_f32=h)
+                    ops.conv_gemm(c_row, lay["cond"], n=2 * C, k=self.n_mels, bias=lay["cond_b"], residual=h, y_f32=h)
+                    _lib.check(L.pk_gated_activation(_ptr(h), rows, C, _ptr(zt.hi), _ptr(zt.lo), st), "pk_gated_activation")
+                    ops.conv_gemm(zt, lay["out"], n=2 * C, k=C, bias=lay["out_b"], y_f32=o)
+                    nxt = bufs[l + 1] if l + 1 < NL else None
+                    _lib.check(L.pk_waveflow_layer_update(_ptr(o), rows, C, _ptr(state), _ptr(skip), 1 if l == 0 else 0,
+                                                          _ptr(nxt.hi) if nxt else None, _ptr(nxt.lo) if nxt else None, 3 * C,
+                                                          slot * C, st), "pk_waveflow_layer_update")
+                _lib.check(L.pk_waveflow_row_out(_ptr(skip), _ptr(fw["out_w"]), _ptr(fw["out_b"]), _ptr(z[:, i]), G * W, B, W, C,
+                                                 _ptr(x[:, i]), G * W, st), "pk_waveflow_row_out")
+            z = x
+        return z.transpose(1, 2).reshape(B, -1)
+
+    def infer(self, mel, z=None):
+        """reference :784-805; the noise z (B, T_c) may be supplied (parity tests), else torch.randn."""
+        if not mel.is_cuda:
+            raise _lib.PkError("ConditionalWaveFlow needs CUDA tensors (no CPU fallback)")
+        condition = self.encode(mel, trim_conv_artifact=True)
+        if z is None:
+            z = torch.randn(condition.shape[0], condition.shape[-1], device=mel.device)
+        return self.inverse(z, condition)
+
+    def predict(self, mel):
+        """reference :807-825: numpy mel (n_mels, T') -> numpy audio."""
+        mel = torch.as_tensor(np.asarray(mel), dtype=torch.float32, device=self.device).unsqueeze(0)
+        return self.infer(mel)[0].cpu().numpy()

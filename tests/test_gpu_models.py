@@ -165,3 +165,24 @@ def test_zscore_and_inference_wrappers(cuda, fs2, pwg):
     wav = PWGInference(norm, gen)(logmel, x=noise)
     assert list(wav.shape) == [logmel.shape[0] * 300, 1] and torch.isfinite(wav).all()
     assert rel_err(wav, gen.inference(mel_n, x=noise)) < 1e-4
+
+
+def test_waveflow_inference_vs_oracle(cuda):
+    """cfg4 architecture (64 channels, 8 flows x 8 layers, n_group 16, upsample 16x16) at a small size, caller-supplied z."""
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    params = owf.synth_params(4)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m.set_state_dict(params)
+    folded = owf.fold_weight_norm(params)
+    g = torch.Generator().manual_seed(4)
+    mel = torch.randn(2, 80, 9, generator=g) * 0.5 - 3
+    cond_ref = owf.encoder(folded, mel, 2)
+    assert list(cond_ref.shape) == [2, 80, 256 * 9 - 272]
+    assert rel_err(m.encode(mel.to(cuda)), cond_ref) < 1e-5
+    z = torch.randn(2, cond_ref.shape[-1], generator=g)
+    with torch.no_grad():
+        ref = owf.infer(folded, mel, z)
+    out = m.infer(mel.to(cuda), z=z.to(cuda))
+    assert list(out.shape) == list(ref.shape)
+    assert rel_err(out, ref) < TOL

@@ -126,3 +126,21 @@ def test_fs2_padding_rows_do_not_leak_in_single_utterance_semantics():
     with torch.no_grad():
         b, a, d, p, e = ofs.fs2_forward(fp, None, xs, il, is_inference=True)
     assert a.shape[1] == int(d.sum()) and (d >= 0).all() and torch.equal(d, torch.round(d))
+
+
+def test_waveflow_oracle_shapes_and_identity_flow():
+    """With the reference's zero-initialised output_proj every flow is the identity up to the row permutations, so
+    inverse(z) is a pure permutation of z - a known answer that pins fold / permutation / unfold index arithmetic."""
+    from oracle import waveflow as owf
+    p = owf.fold_weight_norm(owf.synth_params(4))
+    for k in list(p):
+        if "output_proj" in k:
+            p[k] = torch.zeros_like(p[k])
+    mel = torch.randn(1, 80, 4)
+    cond = owf.encoder(p, mel, 2)
+    assert cond.shape[-1] == 256 * 4 - 272
+    z = torch.arange(cond.shape[-1], dtype=torch.float32)[None]
+    with torch.no_grad():
+        x = owf.infer(p, mel, z)
+    # 8 flows: 4 full reversals + 4 half reversals of the 16 rows compose to the identity permutation
+    assert torch.equal(x, z)
