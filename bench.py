@@ -314,8 +314,28 @@ def main():
             out["extra"] = {"fastspeech2_b32": {"mel_frames_per_s": frames / (fs_ms * 1e-3), "ms_per_step": fs_ms, "frames": frames},
                             "fs2_pwg_e2e_b32": {"samples_per_s": frames * HOP / (tts_ms * 1e-3), "mel_frames_per_s": frames / (tts_ms * 1e-3),
                                                 "ms_per_step": tts_ms, "note": "cfg3, ragged batch, per-GPU"}}
+            # WaveFlow (cfg4): 64 channels, 8 flows x 8 layers, n_group 16, batch 16, 400 mel frames -> 102 128 samples each
+            from parakeet_b200.models import ConditionalWaveFlow
+            wf = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=dev, seed=4)
+            sdw = dict(wf.state_dict())
+            gw = torch.Generator().manual_seed(4)
+            for k_ in sdw:
+                if "output_proj" in k_:      # the reference zero-initialises these (identity flow); use small random values
+                    sdw[k_] = (torch.rand(sdw[k_].shape, generator=gw) * 2 - 1) * 0.05
+            wf.set_state_dict(sdw)
+            melw = (torch.randn(16, 80, FRAMES, generator=gw) * 0.5 - 3).to(dev)
+            zw = torch.randn(16, 256 * FRAMES - 272, generator=gw).to(dev)
+            wf.infer(melw, z=zw)
+            torch.cuda.synchronize()
+            e0.record()
+            aw = wf.infer(melw, z=zw)
+            e1.record()
+            torch.cuda.synchronize()
+            wf_ms = e0.elapsed_time(e1)
+            out["extra"]["waveflow_b16_c64"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
+                                                "note": "cfg4; 5 040 launches per call, launch-bound this round"}
         except Exception as ex:  # extras must never break the headline line
-            out["extra"] = {"error": repr(ex)}
+            out.setdefault("extra", {})["error"] = repr(ex)
         # CPU baseline: the oracle port on the host cores, bounded sample (2 of 32 utterances, ~10-20 s)
         params = {k: v.detach().cpu() for k, v in gen.state_dict().items()}   # same weights, oracle arithmetic
         xs, cs = x_h[:2].clone(), c_h[:2].clone()
