@@ -336,7 +336,8 @@ def main():
                                                 "note": "cfg4; 5 040 launches per call, launch-bound this round"}
         except Exception as ex:  # extras must never break the headline line
             out.setdefault("extra", {})["error"] = repr(ex)
-        # CPU baseline: the oracle port on the host cores, bounded sample (2 of 32 utterances, ~10-20 s)
+    if not args.no_extra and world == 1:
+        # CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample (2 of 32 utterances, ~10-20 s)
         params = {k: v.detach().cpu() for k, v in gen.state_dict().items()}   # same weights, oracle arithmetic
         xs, cs = x_h[:2].clone(), c_h[:2].clone()
         cores = pick_cpu_threads(params, xs, cs)
