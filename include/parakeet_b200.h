@@ -259,6 +259,16 @@ int pk_waveflow_layer_update(const float* o, int64_t rows, int32_t c, float* sta
 int pk_waveflow_row_out(const float* skip, const float* w, const float* bias, const float* z_row, int64_t z_batch_stride,
                         int32_t batch, int32_t width, int32_t c, float* x_next, int64_t x_batch_stride, pk_stream_t stream);
 
+/* FastSpeech2Loss.forward with use_masking=True (models/fastspeech2/fastspeech2.py:701-812; DurationPredictorLoss
+ * duration_predictor.py:140-184): out4 = { l1_loss = L1(before, ys) + L1(after, ys) over valid frames,
+ * duration_loss = MSE(d_outs, log(ds + 1)), pitch_loss = MSE(p_outs, ps), energy_loss = MSE(e_outs, es) over valid tokens }.
+ * before/after/ys (batch, l_max, odim) fp32; d_outs/p_outs/ps/e_outs/es (batch, t_max) fp32; ds int64; workspace12:
+ * device fp32[12] scratch (zeroed by the call). */
+int pk_fs2_loss(const float* before, const float* after, const float* ys, const int32_t* olens, int32_t l_max, int32_t odim,
+                const float* d_outs, const int64_t* ds, const float* p_outs, const float* ps, const float* e_outs,
+                const float* es, const int32_t* ilens, int32_t t_max, int32_t batch, float* workspace12, float* out4,
+                pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ def _declare(L):
         "pk_mask_rows": [vp, vp, i32, i32, i32, vp],
         "pk_variance_embed_add": [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp],
         "pk_zscore": [vp, vp, vp, i32, i64, i32, vp, vp],
+        "pk_fs2_loss": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
         "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],
         "pk_gated_activation": [vp, i64, i32, vp, vp, vp],

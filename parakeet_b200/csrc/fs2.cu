@@ -336,3 +336,88 @@ extern "C" int pk_zscore(const float* x, const float* mu, const float* sigma, in
   count_launch();
   return PK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// FastSpeech2Loss.forward (fastspeech2.py:701-812) with use_masking=True: masked means in one pass.
+//   out[0] = mean_{valid frames x odim} |before - ys| + mean |after - ys|     (L1Loss on masked_select'ed tensors)
+//   out[1] = mean_{valid tokens} (d_outs - log(ds + 1))^2                       (DurationPredictorLoss, offset 1)
+//   out[2] = mean_{valid tokens} (p_outs - ps)^2 ;  out[3] = mean (e_outs - es)^2
+// sums are accumulated in fp32 per block and combined with atomics into 6 accumulators, finalised by the last block.
+// ---------------------------------------------------------------------------------------------------------------
+namespace pk {
+__global__ void __launch_bounds__(256)
+fs2_loss_kernel(const float* __restrict__ before, const float* __restrict__ after, const float* __restrict__ ys,
+                const int32_t* __restrict__ olens, int l_max, int odim, const float* __restrict__ d_outs,
+                const int64_t* __restrict__ ds, const float* __restrict__ p_outs, const float* __restrict__ ps,
+                const float* __restrict__ e_outs, const float* __restrict__ es, const int32_t* __restrict__ ilens, int t_max,
+                int batch, float* __restrict__ acc /*[8]*/, unsigned int* __restrict__ counter, float* __restrict__ out /*[4]*/) {
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long n_mel = static_cast<long long>(batch) * l_max * odim;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_mel; i += stride) {
+    const long long row = i / odim;
+    const int b = row / l_max, t = row % l_max;
+    if (t < __ldg(olens + b)) {
+      const float y = ys[i];
+      s[0] += fabsf(before[i] - y);
+      s[1] += fabsf(after[i] - y);
+    }
+  }
+  const long long n_tok = static_cast<long long>(batch) * t_max;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_tok; i += stride) {
+    const int b = i / t_max, t = i % t_max;
+    if (t < __ldg(ilens + b)) {
+      const float dd = d_outs[i] - logf(static_cast<float>(ds[i]) + 1.0f);
+      const float dp = p_outs[i] - ps[i];
+      const float de = e_outs[i] - es[i];
+      s[2] += dd * dd; s[3] += dp * dp; s[4] += de * de;
+    }
+  }
+  __shared__ float red[5][8];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {   // last block: finalise
+      long long frames = 0, toks = 0;
+      for (int b = 0; b < batch; ++b) { frames += min(olens[b], l_max); toks += min(ilens[b], t_max); }
+      const float nm = static_cast<float>(frames) * odim, nt = static_cast<float>(toks);
+      volatile float* a = acc;
+      out[0] = a[0] / nm + a[1] / nm;
+      out[1] = a[2] / nt;
+      out[2] = a[3] / nt;
+      out[3] = a[4] / nt;
+    }
+  }
+}
+}  // namespace pk
+
+extern "C" int pk_fs2_loss(const float* before, const float* after, const float* ys, const int32_t* olens, int32_t l_max,
+                           int32_t odim, const float* d_outs, const int64_t* ds, const float* p_outs, const float* ps,
+                           const float* e_outs, const float* es, const int32_t* ilens, int32_t t_max, int32_t batch,
+                           float* workspace12, float* out4, pk_stream_t stream) {
+  PK_CHECK_ARG(before && after && ys && olens && d_outs && ds && p_outs && ps && e_outs && es && ilens && workspace12 && out4,
+               "NULL pointer");
+  PK_CHECK_ARG(l_max > 0 && odim > 0 && t_max > 0 && batch > 0, "bad sizes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PK_CHECK_CUDA(cudaMemsetAsync(workspace12, 0, 12 * sizeof(float), s));
+  const long long n = static_cast<long long>(batch) * l_max * odim;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, sm_count() * 4LL));
+  fs2_loss_kernel<<<blocks, 256, 0, s>>>(before, after, ys, olens, l_max, odim, d_outs, ds, p_outs, ps, e_outs, es, ilens, t_max,
+                                         batch, workspace12, reinterpret_cast<unsigned int*>(workspace12 + 8), out4);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}

@@ -423,3 +423,28 @@ class FastSpeech2Inference(Layer):
     def forward(self, text, spk_id=None):
         normalized_mel = self.acoustic_model.inference(text, spk_id=spk_id)
         return self.normalizer.inverse(normalized_mel)
+
+
+class FastSpeech2Loss(Layer):
+    """Loss function module for FastSpeech2 (reference fastspeech2.py:674-812), forward value, use_masking=True."""
+
+    def __init__(self, use_masking: bool = True, use_weighted_masking: bool = False, device=None):
+        super().__init__(device)
+        if not use_masking or use_weighted_masking:
+            raise NotImplementedError("only use_masking=True / use_weighted_masking=False (the shipped yaml) is implemented")
+        self.use_masking, self.use_weighted_masking = use_masking, use_weighted_masking
+
+    def forward(self, after_outs, before_outs, d_outs, p_outs, e_outs, ys, ds, ps, es, ilens, olens):
+        """-> (l1_loss, duration_loss, pitch_loss, energy_loss) as 0-d CUDA tensors (argument order of the reference)."""
+        B, L, odim = ys.shape
+        T = ds.shape[1]
+        dev = ys.device
+        ws = torch.empty(12, dtype=torch.float32, device=dev)
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        f = lambda t: t.contiguous().float()  # noqa: E731
+        _lib.check(_lib.lib().pk_fs2_loss(
+            ops._ptr(f(before_outs)), ops._ptr(f(after_outs)), ops._ptr(f(ys)), ops._ptr(_i32(olens.to(dev))), L, odim,
+            ops._ptr(f(d_outs)), ops._ptr(ds.to(torch.int64).contiguous()), ops._ptr(f(p_outs).reshape(B, T)),
+            ops._ptr(f(ps).reshape(B, T)), ops._ptr(f(e_outs).reshape(B, T)), ops._ptr(f(es).reshape(B, T)),
+            ops._ptr(_i32(ilens.to(dev))), T, B, ops._ptr(ws), ops._ptr(out), ops._stream()), "pk_fs2_loss")
+        return out[0], out[1], out[2], out[3]

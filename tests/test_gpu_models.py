@@ -186,3 +186,18 @@ def test_waveflow_inference_vs_oracle(cuda):
     out = m.infer(mel.to(cuda), z=z.to(cuda))
     assert list(out.shape) == list(ref.shape)
     assert rel_err(out, ref) < TOL
+
+
+def test_fs2_loss_vs_oracle(cuda, fs2):
+    """FastSpeech2Loss (use_masking=True) on the teacher-forced forward of the golden batch."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2Loss
+    m, params = fs2
+    g = np.load(os.path.join(GOLD, "fs2_forward_small.npz"))
+    b = {k: torch.from_numpy(g[k]).to(cuda) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+    before, after, d_outs, p_outs, e_outs, ys, olens = m(b["text"], b["text_lengths"], b["speech"], b["speech_lengths"],
+                                                          b["durations"], b["pitch"], b["energy"])
+    losses = FastSpeech2Loss(device=cuda)(after, before, d_outs, p_outs, e_outs, ys, b["durations"], b["pitch"], b["energy"],
+                                          b["text_lengths"], olens)
+    got = [float(v) for v in losses]
+    assert np.allclose(got, g["losses"], rtol=1e-3), (got, g["losses"])
