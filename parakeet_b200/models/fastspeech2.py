@@ -441,10 +441,15 @@ class FastSpeech2Loss(Layer):
         dev = ys.device
         ws = torch.empty(12, dtype=torch.float32, device=dev)
         out = torch.empty(4, dtype=torch.float32, device=dev)
+        # every converted operand is bound to a local so that it outlives the (asynchronous) launch call: a temporary
+        # freed inside the argument list can be handed out again by the allocator before the kernel is even enqueued
         f = lambda t: t.contiguous().float()  # noqa: E731
-        _lib.check(_lib.lib().pk_fs2_loss(
-            ops._ptr(f(before_outs)), ops._ptr(f(after_outs)), ops._ptr(f(ys)), ops._ptr(_i32(olens.to(dev))), L, odim,
-            ops._ptr(f(d_outs)), ops._ptr(ds.to(torch.int64).contiguous()), ops._ptr(f(p_outs).reshape(B, T)),
-            ops._ptr(f(ps).reshape(B, T)), ops._ptr(f(e_outs).reshape(B, T)), ops._ptr(f(es).reshape(B, T)),
-            ops._ptr(_i32(ilens.to(dev))), T, B, ops._ptr(ws), ops._ptr(out), ops._stream()), "pk_fs2_loss")
+        bo, ao, yy, do_ = f(before_outs), f(after_outs), f(ys), f(d_outs)
+        po, pp = f(p_outs).reshape(B, T), f(ps).reshape(B, T)
+        eo, ee = f(e_outs).reshape(B, T), f(es).reshape(B, T)
+        dsi = ds.to(torch.int64).contiguous()
+        ol, il = _i32(olens.to(dev)), _i32(ilens.to(dev))
+        _lib.check(_lib.lib().pk_fs2_loss(ops._ptr(bo), ops._ptr(ao), ops._ptr(yy), ops._ptr(ol), L, odim, ops._ptr(do_),
+                                          ops._ptr(dsi), ops._ptr(po), ops._ptr(pp), ops._ptr(eo), ops._ptr(ee), ops._ptr(il), T, B,
+                                          ops._ptr(ws), ops._ptr(out), ops._stream()), "pk_fs2_loss")
         return out[0], out[1], out[2], out[3]

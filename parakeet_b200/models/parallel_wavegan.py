@@ -261,7 +261,8 @@ class PWGGenerator(Layer):
         B = c.shape[0]
         frames = c.shape[-1] - 2 * self.aux_context_window
         out = torch.empty(B, self.aux_channels, frames * self.upsample_factor, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().pk_pwg_upsample(_ptr(c.contiguous().float()), _ptr(pk["conv_in_w"]),
+        c = c.contiguous().float()
+        _lib.check(_lib.lib().pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]),
                                               pk["fir_host"].ctypes.data_as(C.c_void_p),
                                               pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
                                               self.aux_channels, frames, self.aux_context_window, None, _ptr(out), None,

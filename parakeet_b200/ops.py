@@ -213,16 +213,18 @@ def transpose_heads(src, col0, dk, heads, ld_dst):
 
 def duration_post(x, lens, offset=1.0):
     B, T = x.shape
+    x = x.contiguous()
     d_f = torch.empty(B, T, dtype=torch.float32, device=x.device)
     d_i = torch.empty(B, T, dtype=torch.int64, device=x.device)
-    _lib.check(_lib.lib().pk_duration_post(_ptr(x.contiguous()), _ptr(lens), B, T, offset, _ptr(d_f), _ptr(d_i), _stream()),
+    _lib.check(_lib.lib().pk_duration_post(_ptr(x), _ptr(lens), B, T, offset, _ptr(d_f), _ptr(d_i), _stream()),
                "pk_duration_post")
     return d_f, d_i
 
 
 def duration_scale(d, alpha):
+    d = d.contiguous()
     out = torch.empty_like(d)
-    _lib.check(_lib.lib().pk_duration_scale(_ptr(d.contiguous()), alpha, d.numel(), _ptr(out), _stream()), "pk_duration_scale")
+    _lib.check(_lib.lib().pk_duration_scale(_ptr(d), alpha, d.numel(), _ptr(out), _stream()), "pk_duration_scale")
     return out
 
 
@@ -235,8 +237,9 @@ def mask_rows_(x, lens):
 
 def variance_embed_add(hs, pitch, energy, wp, bp, we, be, lens=None):
     B, T, c = hs.shape
+    hs, pitch, energy = hs.contiguous(), pitch.contiguous(), energy.contiguous()   # locals: must outlive the launch call
     y = torch.empty_like(hs)
-    _lib.check(_lib.lib().pk_variance_embed_add(_ptr(hs), _ptr(pitch.contiguous()), _ptr(energy.contiguous()), _ptr(wp), _ptr(bp),
+    _lib.check(_lib.lib().pk_variance_embed_add(_ptr(hs), _ptr(pitch), _ptr(energy), _ptr(wp), _ptr(bp),
                                                 wp.shape[-1], _ptr(we), _ptr(be), we.shape[-1], _ptr(lens), B, T, c, _ptr(y),
                                                 _stream()), "pk_variance_embed_add")
     return y
