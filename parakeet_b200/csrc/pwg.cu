@@ -117,9 +117,12 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
   const uint32_t acc1_empty = acc1_full + 16;           // [2]
   const uint32_t acc2_full = acc1_empty + 16;           // [2]
   const uint32_t acc2_empty = acc2_full + 16;           // [2]
-  const uint32_t z_full = acc2_empty + 16;              // [1]
-  const uint32_t g2_free = z_full + 8;                 // [1] producer -> gate warps: the GEMM2 stage of tile i may be written
-  const uint32_t tmem_slot = g2_free + 8;
+  // z_full / g2_free complete once per tile and are double-buffered by tile parity: at the tail of a CTA's tile list the
+  // two last GEMM2 stages are claimed back to back, so a single barrier could advance two phases before a slow waiter
+  // looked at it and the parity wait would alias (observed as a timing-dependent deadlock).
+  const uint32_t z_full = acc2_empty + 16;              // [2] gate warps -> MMA issuer: z of tile i is in its stage
+  const uint32_t g2_free = z_full + 16;                 // [2] producer -> gate warps: the GEMM2 stage of tile i may be written
+  const uint32_t tmem_slot = g2_free + 16;
   // gate constants: [0,64) -2*log2e*bias_a, [64,128) -log2e*bias_g; store biases: [128,256) bias2
   const uint32_t s_bias = bars + 256;
 
@@ -135,8 +138,7 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, kPwgGateWarps * 32);
       mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, kPwgStoreWarps * 32);
     }
-    mbar_init_a(z_full, kPwgGateWarps * 32);
-    mbar_init_a(g2_free, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init_a(z_full + 8 * i, kPwgGateWarps * 32); mbar_init_a(g2_free + 8 * i, 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_a<512>(tmem_slot);
@@ -180,13 +182,15 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
           tma_load_3d_a(st + 3 * kPwgTile, &tm_w1_lo, fb, j * kChunkK, 0, 0);
         }
       };
+      int n_g2 = 0;   // tiles whose GEMM2 stage has been claimed
       auto load_g2 = [&]() {
         const int s = it % kPwgStages;
         PK_TICK(1)
         mbar_wait_a(empty_bar + 8 * s, ((it / kPwgStages) & 1) ^ 1);
         PK_TICK(0)
         const uint32_t st = smem + s * kPwgStageBytes;
-        mbar_arrive_a(g2_free);     // one completion per tile: the gate warps may now write z into this stage's A half
+        mbar_arrive_a(g2_free + 8 * (n_g2 & 1));   // the gate warps may now write z of this tile into the stage's A half
+        ++n_g2;
         mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kPwgTile);
         tma_load_3d_a(st + 2 * kPwgTile, &tm_w2_hi, full_bar + 8 * s, 0, 0, 0);
         tma_load_3d_a(st + 3 * kPwgTile, &tm_w2_lo, full_bar + 8 * s, 0, 0, 0);
@@ -245,7 +249,7 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
         const int buf = i & 1;
         const int s = it % kPwgStages;
         PK_TICK(2)
-        mbar_wait_a(z_full, i & 1);                       // gate warps wrote z into the A half of stage s
+        mbar_wait_a(z_full + 8 * (i & 1), (i >> 1) & 1);   // gate warps wrote z into the A half of stage s
         PK_TICK(3)
         mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
         PK_TICK(4)
@@ -323,9 +327,7 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       }
       PK_TICK(1)
       // The GEMM2 stage of this tile is ours once the producer has claimed it (it waited for the MMA to release it).
-      // g2_free completes exactly once per tile and cannot run more than one tile ahead of this wait (the next claim
-      // needs GEMM2 of this tile, which needs our z), so the parity wait cannot alias.
-      mbar_wait_a(g2_free, i & 1);
+      mbar_wait_a(g2_free + 8 * (i & 1), (i >> 1) & 1);
       PK_TICK(2)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -334,7 +336,7 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
         sts_u4(st2 + kPwgTile + r * kSwizzleBytes + chunk * 16, make_uint4(zl[4 * q], zl[4 * q + 1], zl[4 * q + 2], zl[4 * q + 3]));
       }
       fence_proxy_async_smem();
-      mbar_arrive_a(z_full);
+      mbar_arrive_a(z_full + 8 * (i & 1));
       PK_TICK(3)
       have = have_next; b = nb; m0 = nm0;
     }
