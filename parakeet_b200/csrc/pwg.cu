@@ -26,9 +26,9 @@ namespace pk {
 //   warp 0      TMA producer   : per tile 5 K-chunks for GEMM1 (3 dilated taps of x, 2 chunks of c; A and B = 64 KB
 //                                per stage) + 1 chunk for GEMM2 (W2 only; the A half of that stage receives z)
 //   warp 1      MMA issuer     : G1(0); then per tile { G1(i+1); G2(i) } so GEMM1 of the next tile overlaps the gate
-//   warps 2-9   gate  warps    : acc1 (TMEM) -> tanh * sigmoid -> split-bf16 z tile written (128B-swizzled) into the
+//   warps 4-7   gate  warps    : acc1 (TMEM) -> tanh * sigmoid -> split-bf16 z tile written (128B-swizzled) into the
 //                                A half of the pipeline stage reserved for GEMM2
-//   warps 10-17 store warps    : acc2 (TMEM) -> + bias -> per-warp 32x32 transpose in smem -> coalesced
+//   warps 8-15  store warps    : acc2 (TMEM) -> + bias -> per-warp 32x32 transpose in smem -> coalesced
 //                                red.global.add (skip sum) / residual + split planes (x_out)
 // TMEM: acc1[2] at columns 0/128, acc2[2] at 256/384 (fp32 128x128 each).
 constexpr int kPwgR = 64;        // residual channels
@@ -39,9 +39,10 @@ constexpr int kPwgTile = 128 * kSwizzleBytes;                 // 16 KB: one plan
 constexpr int kPwgStageBytes = 4 * kPwgTile;                  // A hi, A lo, B hi, B lo
 constexpr int kPwgStageSmem = 8 * 32 * kSwizzleBytes;         // 8 store warps x (32 rows x 128 B) transpose slices
 constexpr int kPwgSmem = kPwgStages * kPwgStageBytes + kPwgStageSmem + 1024 + 256 + 1024;  // + align + barriers + biases
-constexpr int kPwgGateWarps = 8;
+constexpr int kPwgGateWarps = 4;
 constexpr int kPwgStoreWarps = 8;
-constexpr int kPwgThreads = 64 + (kPwgGateWarps + kPwgStoreWarps) * 32;   // 576
+constexpr int kPwgFirstGateWarp = 4;                          // warps 2-3 idle: keeps each role on whole warpgroups
+constexpr int kPwgThreads = (kPwgFirstGateWarp + kPwgGateWarps + kPwgStoreWarps) * 32;   // 512 -> 128 registers per thread
 constexpr int kPwgG1Chunks = 5;                               // 3 taps + 2 aux chunks (64 + 16 channels)
 
 struct PwgLayerArgs {
@@ -117,9 +118,6 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
   const uint32_t acc1_empty = acc1_full + 16;           // [2]
   const uint32_t acc2_full = acc1_empty + 16;           // [2]
   const uint32_t acc2_empty = acc2_full + 16;           // [2]
-  // z_full / g2_free complete once per tile and are double-buffered by tile parity: at the tail of a CTA's tile list the
-  // two last GEMM2 stages are claimed back to back, so a single barrier could advance two phases before a slow waiter
-  // looked at it and the parity wait would alias (observed as a timing-dependent deadlock).
   const uint32_t z_full = acc2_empty + 16;              // [2] gate warps -> MMA issuer: z of tile i is in its stage
   const uint32_t g2_free = z_full + 16;                 // [2] producer -> gate warps: the GEMM2 stage of tile i may be written
   const uint32_t tmem_slot = g2_free + 16;
@@ -142,8 +140,8 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_a<512>(tmem_slot);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
-    const int i = threadIdx.x - 64;
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 256) {
+    const int i = threadIdx.x - 128;
     float v;
     if (i < 64) v = -2.f * kLog2e * p.bias1[i];
     else if (i < 128) v = -kLog2e * p.bias1[i];
@@ -276,10 +274,11 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       PK_TICK_FLUSH(8, 7)
       if (kProf) atomicAdd(p.prof + 32, static_cast<unsigned long long>(n_done));
     }
-  } else if (warp < 2 + kPwgGateWarps) {
+  } else if (warp < kPwgFirstGateWarp) {
+    // idle warps
+  } else if (warp < kPwgFirstGateWarp + kPwgGateWarps) {
     // ------------------------------ gate warps ------------------------------
     const int quarter = warp & 3;                 // TMEM lane quarter accessible to this warp
-    const int half = (warp - 2) >> 2;             // z columns [32*half, 32*half + 32)
     const int r = quarter * 32 + lane;            // row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -298,40 +297,47 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
       PK_TICK(0)
       tcgen05_fence_after();
-      float va[32], vb[32];
-      __syncwarp();
-      tmem_ld_32x32(tmem_base + lane_base + buf * 128 + half * 32, va);
-      tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive_a(acc1_empty + 8 * buf);
-      // z = tanh(a + ba) * sigmoid(g + bg) = (1 - e1) / ((1 + e1)(1 + e2)), e1 = exp(-2(a+ba)), e2 = exp(-(g+bg))
-      // (one reciprocal; the exp2 argument of e1 is clamped at 60 so that the product cannot overflow where z != 0)
-      uint32_t zh[16], zl[16];
+      uint32_t zh[32], zl[32];                    // 64 z columns of this thread's row, packed bf16x2 hi / lo
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 ca = lds_const_f4(s_bias + 4 * (half * 32 + j));
-        const float4 cg = lds_const_f4(s_bias + 4 * (64 + half * 32 + j));
-        const float cav[4] = {ca.x, ca.y, ca.z, ca.w};
-        const float cgv[4] = {cg.x, cg.y, cg.z, cg.w};
-        float z[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float e1 = exp2f(fminf(fmaf(va[j + e], -2.f * kLog2e, cav[e]), 60.f));
-          const float e2 = exp2f(fmaf(vb[j + e], -kLog2e, cgv[e]));
-          const float den = fmaf(e1, e2, e1 + e2) + 1.f;
-          z[e] = __fdividef(1.f - e1, den);
+      for (int half = 0; half < 2; ++half) {
+        float va[32], vb[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + half * 32, va);
+        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
+        tmem_ld_wait();
+        if (half == 1) {
+          tcgen05_fence_before();
+          mbar_arrive_a(acc1_empty + 8 * buf);
         }
-        split2(z[0], z[1], zh[j / 2], zl[j / 2]);
-        split2(z[2], z[3], zh[j / 2 + 1], zl[j / 2 + 1]);
+        // z = tanh(a + ba) * sigmoid(g + bg) = (1 - e1) / ((1 + e1)(1 + e2)), e1 = exp(-2(a+ba)), e2 = exp(-(g+bg))
+        // (one reciprocal; the exp2 argument of e1 is clamped at 60 so that the product cannot overflow where z != 0)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ca = lds_const_f4(s_bias + 4 * (half * 32 + j));
+          const float4 cg = lds_const_f4(s_bias + 4 * (64 + half * 32 + j));
+          const float cav[4] = {ca.x, ca.y, ca.z, ca.w};
+          const float cgv[4] = {cg.x, cg.y, cg.z, cg.w};
+          float z[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float e1 = exp2f(fminf(fmaf(va[j + e], -2.f * kLog2e, cav[e]), 60.f));
+            const float e2 = exp2f(fmaf(vb[j + e], -kLog2e, cgv[e]));
+            const float den = fmaf(e1, e2, e1 + e2) + 1.f;
+            z[e] = __fdividef(1.f - e1, den);
+          }
+          split2(z[0], z[1], zh[half * 16 + j / 2], zl[half * 16 + j / 2]);
+          split2(z[2], z[3], zh[half * 16 + j / 2 + 1], zl[half * 16 + j / 2 + 1]);
+        }
       }
       PK_TICK(1)
       // The GEMM2 stage of this tile is ours once the producer has claimed it (it waited for the MMA to release it).
+      // g2_free completes exactly once per tile and cannot run more than one tile ahead of this wait (the next claim
+      // needs GEMM2 of this tile, which needs our z), so the parity wait cannot alias.
       mbar_wait_a(g2_free + 8 * (i & 1), (i >> 1) & 1);
       PK_TICK(2)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = (half * 4 + q) ^ (r & 7);  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+      for (int q = 0; q < 8; ++q) {
+        const int chunk = q ^ (r & 7);               // 128B swizzle: 16-byte chunk index XOR (row mod 8)
         sts_u4(st2 + r * kSwizzleBytes + chunk * 16, make_uint4(zh[4 * q], zh[4 * q + 1], zh[4 * q + 2], zh[4 * q + 3]));
         sts_u4(st2 + kPwgTile + r * kSwizzleBytes + chunk * 16, make_uint4(zl[4 * q], zl[4 * q + 1], zl[4 * q + 2], zl[4 * q + 3]));
       }
@@ -341,10 +347,10 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
       have = have_next; b = nb; m0 = nm0;
     }
     PK_TICK(6)
-    if (lane == 0 && quarter == 0) { PK_TICK_FLUSH(16 + half * 8, 7) }
+    if (lane == 0 && quarter == 0) { PK_TICK_FLUSH(16, 7) }
   } else {
     // ------------------------------ store warps ------------------------------
-    const int sw = warp - 2 - kPwgGateWarps;      // 0..7
+    const int sw = warp - kPwgFirstGateWarp - kPwgGateWarps;   // 0..7
     const int quarter = warp & 3;
     const int half = sw >> 2;                     // 0: skip columns (acc2 cols 0..63), 1: out columns (64..127)
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
