@@ -90,6 +90,17 @@ struct PwgTileIter {
   }
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, 2 ulp; inf for x > 128, 0 for x < -150
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp; rcp(inf) = 0
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // split two fp32 values into packed bf16x2 hi / lo words (cvt.rn.bf16x2.f32: one instruction per pair)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -320,10 +331,10 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
           float z[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float e1 = exp2f(fminf(fmaf(va[j + e], -2.f * kLog2e, cav[e]), 60.f));
-            const float e2 = exp2f(fmaf(vb[j + e], -kLog2e, cgv[e]));
+            const float e1 = ex2_approx(fminf(fmaf(va[j + e], -2.f * kLog2e, cav[e]), 60.f));
+            const float e2 = ex2_approx(fmaf(vb[j + e], -kLog2e, cgv[e]));
             const float den = fmaf(e1, e2, e1 + e2) + 1.f;
-            z[e] = __fdividef(1.f - e1, den);
+            z[e] = (1.f - e1) * rcp_approx(den);
           }
           split2(z[0], z[1], zh[half * 16 + j / 2], zl[half * 16 + j / 2]);
           split2(z[2], z[3], zh[half * 16 + j / 2 + 1], zl[half * 16 + j / 2 + 1]);
