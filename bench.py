@@ -246,7 +246,7 @@ def main():
                 "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact config (B=32, 400 frames), from
                 # `ncu --set full` (profiles/r01_pwg_layer_final_b32_ncu.txt); algorithmic bytes are 5.16e9
-                "traffic": 5.208e9, "traffic_unit": "bytes/launch",
+                "traffic": 5.169e9, "traffic_unit": "bytes/launch",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launch_ms": layer_launch_ms, "launches_per_step": 30,
                 "note": "algorithmic FLOPs; split-bf16 operands execute 3 tensor-core passes per product",
