@@ -152,3 +152,29 @@ def synth_params(seed=4, upsample_factors=(16, 16), n_flows=8, n_layers=8, n_gro
                 q[k] = v
         return q
     return p
+
+
+def flow_forward(p, pre, x, condition, n_layers, n_group, kernel_size=(3, 3)):
+    """Flow.forward (:465-494) with the full (non-incremental) ResidualBlock.forward (:209-226): causal padding
+    [rh-1, 0] along the height, 'same' along the width.  Used only as the self-consistency check inverse(forward(x)) == x."""
+    dil_h = DILATIONS_H[n_group]
+    h = F.conv2d(x[:, :, :-1], p[pre + "input_proj.weight"], p[pre + "input_proj.bias"])
+    cond = condition[:, :, 1:]
+    skips = 0
+    for l in range(n_layers):
+        q = f"{pre}resnet.{l}."
+        dil = (dil_h[l], 2 ** l)
+        rh = 1 + (kernel_size[0] - 1) * dil[0]
+        rw = 1 + (kernel_size[1] - 1) * dil[1]
+        y = F.conv2d(F.pad(h, (rw // 2, (rw - 1) // 2, rh - 1, 0)), p[q + "conv.weight"], p[q + "conv.bias"], dilation=dil)
+        y = y + F.conv2d(cond, p[q + "condition_proj.weight"], p[q + "condition_proj.bias"])
+        content, gate = torch.chunk(y, 2, dim=1)
+        y = torch.tanh(content) * torch.sigmoid(gate)
+        y = F.conv2d(y, p[q + "out_proj.weight"], p[q + "out_proj.bias"])
+        res, skip = torch.chunk(y, 2, dim=1)
+        h = h + res
+        skips = skips + skip
+    params = F.conv2d(skips, p[pre + "output_proj.weight"], p[pre + "output_proj.bias"])
+    logs, b = torch.chunk(params, 2, dim=1)
+    z = torch.cat([x[:, :, :1], x[:, :, 1:] * torch.exp(logs) + b], dim=2)   # _transform :456-463
+    return z, logs

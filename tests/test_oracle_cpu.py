@@ -144,3 +144,18 @@ def test_waveflow_oracle_shapes_and_identity_flow():
         x = owf.infer(p, mel, z)
     # 8 flows: 4 full reversals + 4 half reversals of the 16 rows compose to the identity permutation
     assert torch.equal(x, z)
+
+
+def test_waveflow_flow_forward_inverse_identity():
+    """SURVEY 8c cross-check 4: Flow.inverse (incremental 3-row cache) undoes Flow.forward (full causal convolution) -
+    a known-answer test the reference's own math guarantees, tying the row-cache restatement to the conv definition."""
+    from oracle import waveflow as owf
+    torch.manual_seed(0)
+    p = owf.fold_weight_norm(owf.synth_params(4, n_flows=2, n_layers=8))
+    x = torch.randn(2, 1, 16, 23)
+    cond = torch.randn(2, 80, 16, 23)
+    with torch.no_grad():
+        z, logs = owf.flow_forward(p, "decoder.0.", x, cond, 8, 16)
+        x_back = owf.flow_inverse(p, "decoder.0.", z, cond, 8, 16)
+    assert logs.abs().max() > 1e-3                      # the flow is not the identity
+    assert (x_back - x).abs().max().item() < 1e-4
