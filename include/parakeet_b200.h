@@ -269,6 +269,57 @@ int pk_fs2_loss(const float* before, const float* after, const float* ys, const 
                 const float* es, const int32_t* ilens, int32_t t_max, int32_t batch, float* workspace12, float* out4,
                 pk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * FastSpeech2 training step (reference: FastSpeech2Updater.update_core, models/fastspeech2/fastspeech2_updater.py:51-99:
+ * forward, FastSpeech2Loss, loss.backward(), optimizer.step(); DataParallel gradient averaging is one NCCL all-reduce
+ * on the flat gradient buffer, issued by the host through torch.distributed).  GEMM-shaped gradients reuse
+ * pk_conv_gemm: dgrad = conv with flipped taps, wgrad / attention gradients = NT matmuls on transposed split planes.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* dst[z*dst_zstride + c*ld_dst + r] = src[z*src_zstride + (r + shift)*ld_src + c0 + c] for r in [0, r_out), c in [0, cols)
+ * (0 where r + shift is outside [0, rows)); split planes.  Builds K-major operands (X^T, dY^T, K^T, dS^T ...). */
+int pk_transpose_planes(const void* src_hi, const void* src_lo, int32_t z, int32_t rows, int64_t src_zstride, int32_t ld_src,
+                        int32_t c0, int32_t cols, int32_t shift, int32_t r_out, void* dst_hi, void* dst_lo, int64_t dst_zstride,
+                        int64_t ld_dst, pk_stream_t stream);
+/* LayerNorm backward: dx (+)= d/dx, dgamma += sum dy*xhat, dbeta += sum dy (fp32 [d], accumulated atomically). */
+int pk_layer_norm_bwd(const float* x, const float* gamma, const float* dy, float eps, int64_t rows, int32_t d, float* dx,
+                      int32_t accumulate, float* dgamma, float* dbeta, pk_stream_t stream);
+/* softmax backward: ds = scale * p * (dp - sum_k p dp) over the first `keys` columns of rows of pitch ld (rest -> 0). */
+int pk_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, int64_t rows, int32_t keys, int32_t ld, float scale,
+                   void* ds_hi, void* ds_lo, pk_stream_t stream);
+/* out[c] += sum_rows x[row, c] (bias gradients). */
+int pk_colsum(const float* x, int64_t rows, int32_t c, float* out, pk_stream_t stream);
+/* BatchNorm1D in training mode on (rows, c) (tacotron2/decoder.py:128-180 under model.train()): batch statistics
+ * (biased variance), y = act(gamma * xhat + beta) with act in {PK_ACT_NONE, PK_ACT_TANH}, running statistics updated with
+ * Paddle's momentum (running = momentum * running + (1 - momentum) * batch); saves mean / rstd for the backward. */
+int pk_batch_norm_train(const float* x, int64_t rows, int32_t c, const float* gamma, const float* beta, float eps, int32_t act,
+                        float momentum, float* run_mean, float* run_var, float* sums2c, float* y, void* y_hi, void* y_lo,
+                        float* save_mean, float* save_rstd, pk_stream_t stream);
+/* backward of the above (including the tanh): dx; afterwards sums2c = { dbeta[c], dgamma[c] }. */
+int pk_batch_norm_bwd(const float* x, const float* dy, const float* y_act, const float* mean, const float* rstd, const float* gamma,
+                      int32_t act, int64_t rows, int32_t c, float* sums2c, float* dx, pk_stream_t stream);
+/* dx = dy * (y > 0), y given by the hi plane of the saved ReLU output; fp32 and/or split output. */
+int pk_relu_bwd(const float* dy, const void* y_hi, int64_t n, float* dx, void* dx_hi, void* dx_lo, pk_stream_t stream);
+/* y += a * x */
+int pk_axpy(float a, const float* x, int64_t n, float* y, pk_stream_t stream);
+/* gradients of l1_loss + duration_loss + pitch_loss + energy_loss (pk_fs2_loss) w.r.t. before, after, d_outs, p_outs, e_outs */
+int pk_fs2_loss_bwd(const float* before, const float* after, const float* ys, const int32_t* olens, int32_t l_max, int32_t odim,
+                    const float* d_outs, const int64_t* ds, const float* p_outs, const float* ps, const float* e_outs,
+                    const float* es, const int32_t* ilens, int32_t t_max, int32_t batch, float* g_before, float* g_after,
+                    float* g_d, float* g_p, float* g_e, pk_stream_t stream);
+/* backward of pk_embed_pe: dtable[ids] += dx (ids may be NULL: positional encoding only), dalpha += sum dx * PE */
+int pk_embed_pe_bwd(const int64_t* ids, const float* dx, int32_t vocab, int32_t padding_idx, int32_t batch, int32_t t, int32_t d,
+                    float* dtable, float* dalpha, pk_stream_t stream);
+/* backward of pk_length_regulate: dx[b, j, :] = sum over the frames of token j of dy[b, frame, :] */
+int pk_length_regulate_bwd(const float* dy, const int64_t* dur, int32_t batch, int32_t t_in, int32_t c, int32_t t_out, float* dx,
+                           pk_stream_t stream);
+/* weight / bias gradients of pitch_embed / energy_embed (Conv1D(1 -> c, k) on a scalar track): dw [c][k], db [c] accumulated */
+int pk_scalar_conv_wgrad(const float* dhs, const float* track, int32_t batch, int32_t t, int32_t c, int32_t k, float* dw, float* db,
+                         pk_stream_t stream);
+/* paddle.optimizer.Adam step on a flat buffer (training/optimizer.py:17-46): g * grad_scale (1/world for DataParallel),
+ * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), p -= lr_t * m / (sqrt(v) + eps * sqrt(1 - beta2^t)). */
+int pk_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+            int32_t step, float grad_scale, pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

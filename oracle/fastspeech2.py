@@ -184,12 +184,25 @@ def length_regulator(xs, ds, alpha=1.0):
     return length_regulator_expand(xs, ds.to(torch.int64))
 
 
-def postnet(p, xs, n_layers):
-    """Postnet.forward (tacotron2/decoder.py:182-198) on (B, odim, T); BatchNorm in eval mode; dropout identity."""
+def postnet(p, xs, n_layers, train_bn=False, new_stats=None):
+    """Postnet.forward (tacotron2/decoder.py:182-198) on (B, odim, T); dropout identity.  BatchNorm1D in eval mode uses the
+    running statistics; with train_bn=True (model.train()) it uses the batch statistics (biased variance) and the updated
+    running statistics (paddle momentum 0.9: running = 0.9 * running + 0.1 * batch, biased variance) go to `new_stats`."""
     for i in range(n_layers):
         w = p[f"postnet.postnet.{i}.0.weight"]
         xs = F.conv1d(xs, w, None, padding=(w.shape[-1] - 1) // 2)
         pre = f"postnet.postnet.{i}.1."
+        if train_bn:
+            mean = xs.mean(dim=(0, 2))
+            var = xs.var(dim=(0, 2), unbiased=False)
+            if new_stats is not None:
+                new_stats[pre + "_mean"] = (0.9 * p[pre + "_mean"] + 0.1 * mean).detach()
+                new_stats[pre + "_variance"] = (0.9 * p[pre + "_variance"] + 0.1 * var).detach()
+            xs = (xs - mean[None, :, None]) / torch.sqrt(var[None, :, None] + 1e-5) * p[pre + "weight"][None, :, None] \
+                + p[pre + "bias"][None, :, None]
+            if i != n_layers - 1:
+                xs = torch.tanh(xs)
+            continue
         xs = F.batch_norm(xs, p[pre + "_mean"], p[pre + "_variance"], p[pre + "weight"], p[pre + "bias"], False, 0.0, 1e-5)
         if i != n_layers - 1:
             xs = torch.tanh(xs)
@@ -197,7 +210,8 @@ def postnet(p, xs, n_layers):
 
 
 def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0,
-                return_intermediates=False):
+                return_intermediates=False, train_bn=False, new_stats=None, stop_gradient_from_pitch_predictor=False,
+                stop_gradient_from_energy_predictor=False):
     """FastSpeech2._forward (fastspeech2.py:377-466), single speaker, no tones.
 
     xs (B,Tmax) int64; ilens (B,); training: olens (B,), ds (B,Tmax) int64, ps/es (B,Tmax,1).
@@ -208,8 +222,11 @@ def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inf
     x_masks = make_non_pad_mask(ilens, xs.shape[1]).unsqueeze(-2)          # _source_mask :618-641
     hs = encoder(p, "encoder.", xs, x_masks, cfg["elayers"], nh, embed=True)
     d_masks = make_pad_mask(ilens, xs.shape[1])
-    p_outs = variance_predictor(p, "pitch_predictor.", hs, d_masks.unsqueeze(-1), cfg["pitch_predictor_layers"])
-    e_outs = variance_predictor(p, "energy_predictor.", hs, d_masks.unsqueeze(-1), cfg["energy_predictor_layers"])
+    # fastspeech2.py:412-419 (stop_gradient_from_*_predictor -> hs.detach())
+    p_outs = variance_predictor(p, "pitch_predictor.", hs.detach() if stop_gradient_from_pitch_predictor else hs,
+                                d_masks.unsqueeze(-1), cfg["pitch_predictor_layers"])
+    e_outs = variance_predictor(p, "energy_predictor.", hs.detach() if stop_gradient_from_energy_predictor else hs,
+                                d_masks.unsqueeze(-1), cfg["energy_predictor_layers"])
     if is_inference:
         d_outs = duration_predictor(p, "duration_predictor.", hs, d_masks, cfg["duration_predictor_layers"], True)
         p_embs = conv1d_cl(p, "pitch_embed.0", p_outs)
@@ -231,7 +248,7 @@ def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inf
     if cfg["postnet_layers"] == 0:
         after_outs = before_outs
     else:
-        after_outs = before_outs + postnet(p, before_outs.transpose(1, 2), cfg["postnet_layers"]).transpose(1, 2)
+        after_outs = before_outs + postnet(p, before_outs.transpose(1, 2), cfg["postnet_layers"], train_bn, new_stats).transpose(1, 2)
     if return_intermediates:
         return before_outs, after_outs, d_outs, p_outs, e_outs, dict(hs=hs, hs_lr=hs_lr, zs=zs)
     return before_outs, after_outs, d_outs, p_outs, e_outs
@@ -370,3 +387,42 @@ def synth_train_batch(seed, lengths, odim=80, idim=80, dur_range=(2, 12)):
         ps[b, :n] = torch.randn(n, 1, generator=g)
         es[b, :n] = torch.randn(n, 1, generator=g)
     return dict(text=xs, text_lengths=ilens, speech=ys, speech_lengths=olens, durations=ds, pitch=ps, energy=es)
+
+
+# ----------------------------------------------------------------------------------------
+# Training step restatement (FastSpeech2Updater.update_core, fastspeech2_updater.py:51-99): forward in train mode with
+# dropout off, FastSpeech2Loss, torch autograd for loss.backward(), paddle.optimizer.Adam semantics.
+# ----------------------------------------------------------------------------------------
+BUFFER_SUFFIXES = ("_mean", "_variance")
+
+
+def train_step_grads(p, cfg, batch, stop_gradient_from_pitch_predictor=True, stop_gradient_from_energy_predictor=False):
+    """-> (losses dict, grads dict keyed like p (trainable tensors only), new BN running stats)."""
+    q = {k: (v.clone().requires_grad_(True) if not k.endswith(BUFFER_SUFFIXES) else v.clone()) for k, v in p.items()}
+    new_stats = {}
+    out = fs2_forward(q, cfg, batch["text"], batch["text_lengths"], batch["speech_lengths"], batch["durations"], batch["pitch"],
+                      batch["energy"], train_bn=True, new_stats=new_stats,
+                      stop_gradient_from_pitch_predictor=stop_gradient_from_pitch_predictor,
+                      stop_gradient_from_energy_predictor=stop_gradient_from_energy_predictor)
+    l1, dur, pitch, energy = fs2_loss(out[1], out[0], out[2], out[3], out[4], batch["speech"], batch["durations"], batch["pitch"],
+                                      batch["energy"], batch["text_lengths"], batch["speech_lengths"])
+    loss = l1 + dur + pitch + energy                                           # fastspeech2_updater.py:83
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in q.items() if not k.endswith(BUFFER_SUFFIXES)}
+    losses = dict(l1_loss=float(l1), duration_loss=float(dur), pitch_loss=float(pitch), energy_loss=float(energy), loss=float(loss))
+    return losses, grads, new_stats
+
+
+def adam_step(p, grads, state, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    """paddle.optimizer.Adam (training/optimizer.py:17-46): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps*sqrt(1-b2^t))."""
+    state["t"] = state.get("t", 0) + 1
+    t = state["t"]
+    c1, c2 = 1 - beta1 ** t, math.sqrt(1 - beta2 ** t)
+    out = dict(p)
+    for k, g in grads.items():
+        m = state.setdefault("m." + k, torch.zeros_like(g))
+        v = state.setdefault("v." + k, torch.zeros_like(g))
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        out[k] = p[k] - (lr * c2 / c1) * m / (v.sqrt() + eps * c2)
+    return out

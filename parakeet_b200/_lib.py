@@ -79,6 +79,19 @@ def _declare(L):
         "pk_variance_embed_add": [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp],
         "pk_zscore": [vp, vp, vp, i32, i64, i32, vp, vp],
         "pk_fs2_loss": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp],
+        "pk_transpose_planes": [vp, vp, i32, i32, i64, i32, i32, i32, i32, i32, vp, vp, i64, i64, vp],
+        "pk_layer_norm_bwd": [vp, vp, vp, f32, i64, i32, vp, i32, vp, vp, vp],
+        "pk_softmax_bwd": [vp, vp, vp, i64, i32, i32, f32, vp, vp, vp],
+        "pk_colsum": [vp, i64, i32, vp, vp],
+        "pk_batch_norm_train": [vp, i64, i32, vp, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "pk_batch_norm_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp],
+        "pk_relu_bwd": [vp, vp, i64, vp, vp, vp, vp],
+        "pk_axpy": [f32, vp, i64, vp, vp],
+        "pk_fs2_loss_bwd": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp],
+        "pk_embed_pe_bwd": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
+        "pk_length_regulate_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
+        "pk_scalar_conv_wgrad": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
+        "pk_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
         "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
         "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],
         "pk_gated_activation": [vp, i64, i32, vp, vp, vp],

@@ -251,3 +251,43 @@ def zscore(x, mu, sigma, inverse=False):
     _lib.check(_lib.lib().pk_zscore(_ptr(x), _ptr(mu), _ptr(sigma), x.shape[-1], x.numel(), 1 if inverse else 0, _ptr(y), _stream()),
                "pk_zscore")
     return y
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training-step helpers (train.cu)
+# ----------------------------------------------------------------------------------------------------------------
+def transpose_planes(src, *, z, rows, src_zstride, ld_src, c0, cols, shift, r_out, dst, dst_zstride, ld_dst):
+    """dst[z*dst_zstride + c*ld_dst + r] = src[z*src_zstride + (r+shift)*ld_src + c0 + c]; src / dst are Split (views allowed)."""
+    _lib.check(_lib.lib().pk_transpose_planes(_ptr(src.hi), _ptr(src.lo), z, rows, src_zstride, ld_src, c0, cols, shift, r_out,
+                                              _ptr(dst.hi), _ptr(dst.lo), dst_zstride, ld_dst, _stream()), "pk_transpose_planes")
+
+
+def layer_norm_bwd(x, gamma, dy, dx, accumulate, dgamma, dbeta, eps=1e-5):
+    rows, d = x.numel() // x.shape[-1], x.shape[-1]
+    _lib.check(_lib.lib().pk_layer_norm_bwd(_ptr(x), _ptr(gamma), _ptr(dy), eps, rows, d, _ptr(dx), 1 if accumulate else 0,
+                                            _ptr(dgamma), _ptr(dbeta), _stream()), "pk_layer_norm_bwd")
+
+
+def softmax_bwd(p, dp, keys, scale):
+    ld = dp.shape[-1]
+    rows = dp.numel() // ld
+    ds = Split.empty(tuple(dp.shape), dp.device)
+    _lib.check(_lib.lib().pk_softmax_bwd(_ptr(p.hi), _ptr(p.lo), _ptr(dp), rows, keys, ld, scale, _ptr(ds.hi), _ptr(ds.lo), _stream()),
+               "pk_softmax_bwd")
+    return ds
+
+
+def colsum_(x, out):
+    c = x.shape[-1]
+    _lib.check(_lib.lib().pk_colsum(_ptr(x), x.numel() // c, c, _ptr(out), _stream()), "pk_colsum")
+
+
+def relu_bwd(dy, y_split, want_f32=False):
+    dx = torch.empty_like(dy) if want_f32 else None
+    dxs = Split.empty(tuple(dy.shape), dy.device)
+    _lib.check(_lib.lib().pk_relu_bwd(_ptr(dy), _ptr(y_split.hi), dy.numel(), _ptr(dx), _ptr(dxs.hi), _ptr(dxs.lo), _stream()), "pk_relu_bwd")
+    return dx, dxs
+
+
+def axpy_(a, x, y):
+    _lib.check(_lib.lib().pk_axpy(float(a), _ptr(x), x.numel(), _ptr(y), _stream()), "pk_axpy")

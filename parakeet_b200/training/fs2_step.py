@@ -1,0 +1,409 @@
+"""FastSpeech2 training step on B200 (reference: FastSpeech2Updater.update_core, parakeet/models/fastspeech2/
+fastspeech2_updater.py:51-99; data-parallel set-up examples/fastspeech2/train.py:51-56,135-139).
+
+    forward (train mode: BatchNorm uses batch statistics, dropout probability 0 as in SURVEY.md 8d)
+    -> FastSpeech2Loss (use_masking=True) -> backward -> mean all-reduce of the gradients over ranks (DataParallel)
+    -> paddle.optimizer.Adam step.
+
+All parameters live in ONE flat fp32 buffer (the model's state-dict entries are views into it), all gradients in a second
+flat buffer: the data-parallel exchange is a single NCCL all-reduce of that buffer per step over NVLink, the 1/world
+scale is folded into the fused Adam kernel (pk_adam).  Every FLOP runs in libparakeet_b200.so: GEMM-shaped gradients
+(dgrad = conv with flipped taps, wgrad = dY^T X over the flattened batch x time axis, attention dQ/dK/dV/dP) reuse
+pk_conv_gemm on transposed split planes (pk_transpose_planes); the rest are the row-wise kernels of train.cu.
+torch is used for buffers, views, permutes / copies (layout plumbing) and torch.distributed.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib, ops
+from ..models.fastspeech2 import FastSpeech2, _i32
+from ..ops import Split, _ptr, _stream
+
+BUFFERS = ("_mean", "_variance")
+
+
+def _ceil64(n):
+    return (n + 63) // 64 * 64
+
+
+def pack_dev(w):
+    """[n, k, taps] (or [n, k]) fp32 CUDA tensor -> K-major split planes [n, taps * Kp] (device-side ops.pack_weight)."""
+    if w.dim() == 2:
+        w = w.unsqueeze(-1)
+    n, k, taps = w.shape
+    kp = _ceil64(k)
+    packed = torch.zeros(n, taps, kp, dtype=torch.float32, device=w.device)
+    packed[:, :, :k] = w.permute(0, 2, 1)
+    return Split.from_f32(packed.reshape(n, taps * kp))
+
+
+class FastSpeech2TrainStep:
+    def __init__(self, model: FastSpeech2, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8,
+                 stop_gradient_from_pitch_predictor=None, stop_gradient_from_energy_predictor=None, process_group=None):
+        if not model.device.type == "cuda":
+            raise _lib.PkError("training needs a CUDA device (no CPU fallback)")
+        self.m = model
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
+        self.sg_pitch = model.stop_gradient_from_pitch_predictor if stop_gradient_from_pitch_predictor is None else stop_gradient_from_pitch_predictor
+        self.sg_energy = model.stop_gradient_from_energy_predictor if stop_gradient_from_energy_predictor is None else stop_gradient_from_energy_predictor
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        dev = model.device
+        names = [k for k in model._params if not k.endswith(BUFFERS)]
+        sizes = [model._params[k].numel() for k in names]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += (s + 3) // 4 * 4                      # keep every view 16-byte aligned
+        self.flat = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.grads = {}
+        for k, o, s in zip(names, offs, sizes):
+            shape = model._params[k].shape
+            self.flat[o:o + s].copy_(model._params[k].reshape(-1))
+            model._params[k] = self.flat[o:o + s].view(shape)      # the model now reads the flat buffer
+            self.grads[k] = self.gflat[o:o + s].view(shape)
+        model._packed = None
+        self.step_count = 0
+        self.sums = torch.zeros(4096, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # GEMM-shaped forward / backward pieces
+    # ------------------------------------------------------------------------------------------------------------
+    def P(self, name):
+        return self.m._params[name]
+
+    def _pack(self, key, fn):
+        v = self._packs.get(key)
+        if v is None:
+            v = self._packs[key] = fn()
+        return v
+
+    def w_fwd(self, name, kind):
+        w = self.P(name)
+        return self._pack(("f", name), lambda: pack_dev(w.t().contiguous() if kind == "lin" else w))
+
+    def w_bwd(self, name, kind):
+        w = self.P(name)
+        return self._pack(("b", name), lambda: pack_dev(w if kind == "lin" else w.flip(-1).permute(1, 0, 2).contiguous()))
+
+    def dims(self, name, kind):
+        w = self.P(name)
+        return (w.shape[0], w.shape[1], 1) if kind == "lin" else (w.shape[1], w.shape[0], w.shape[2])   # (cin, cout, taps)
+
+    def layer_fwd(self, x, wname, bname, kind, act=None, residual=None, f32=True, split=False):
+        cin, cout, taps = self.dims(wname, kind)
+        return ops.conv_gemm(x, self.w_fwd(wname, kind), n=cout, k=cin, taps=taps, bias=self.P(bname) if bname else None, act=act,
+                             residual=residual, out_f32=f32, out_split=split)
+
+    def layer_bwd(self, dy, x_saved, wname, bname, kind, need_dx=True):
+        """dy fp32 (B,T,cout), x_saved split (B,T,cin): accumulates grads of weight / bias, returns dx fp32 (B,T,cin)."""
+        cin, cout, taps = self.dims(wname, kind)
+        B, T = dy.shape[0], dy.shape[1]
+        if cout % 8:
+            dy8 = torch.zeros(B, T, (cout + 7) // 8 * 8, dtype=torch.float32, device=dy.device)   # TMA row pitch: 16 bytes
+            dy8[..., :cout] = dy
+            dys = Split.from_f32(dy8)
+        else:
+            dys = Split.from_f32(dy)
+        if bname:
+            ops.colsum_(dy.reshape(B * T, cout), self.grads[bname])
+        dx = None
+        if need_dx:
+            dx, _ = ops.conv_gemm(dys, self.w_bwd(wname, kind), n=cin, k=cout, taps=taps)
+        self.wgrad(x_saved, dys, wname, kind, cin, cout, taps)
+        return dx
+
+    def wgrad(self, x, dys, wname, kind, cin, cout, taps):
+        B, T = x.hi.shape[0], x.hi.shape[1]
+        Tp = _ceil64(T)
+        KK = B * Tp
+        dev = x.hi.device
+        dyt = Split.zeros((cout, KK), dev)
+        ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * dys.hi.shape[2], ld_src=dys.hi.shape[2], c0=0, cols=cout, shift=0,
+                             r_out=T, dst=dyt, dst_zstride=Tp, ld_dst=KK)
+        pad = (taps - 1) // 2
+        tmp = torch.empty(taps, cout, cin, dtype=torch.float32, device=dev) if kind == "conv" else None
+        for tap in range(taps):
+            xt = Split.zeros((cin, KK), dev)
+            ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin, shift=tap - pad,
+                                 r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KK)
+            sx = dict(rows=cin, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
+            sy = dict(rows=cout, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
+            if kind == "lin":    # Paddle Linear weight [in, out]
+                ops.batched_matmul_nt(xt, dyt, batch=1, heads=1, m=cin, n=cout, k=KK, a_spec=sx, b_spec=sy, y_f32=self.grads[wname],
+                                      y_batch_stride=0, y_head_stride=0, y_ld=cout)
+            else:                # Conv1D weight [out, in, k]
+                ops.batched_matmul_nt(dyt, xt, batch=1, heads=1, m=cout, n=cin, k=KK, a_spec=sy, b_spec=sx, y_f32=tmp[tap],
+                                      y_batch_stride=0, y_head_stride=0, y_ld=cin)
+        if kind == "conv":
+            self.grads[wname].copy_(tmp.permute(1, 2, 0))
+
+    # ------------------------------------------------------------------------------------------------------------
+    # FFT-block stack (Encoder.forward after the embedding) with saved context
+    # ------------------------------------------------------------------------------------------------------------
+    def stack_fwd(self, x, pre, n_layers, key_lens):
+        m = self.m
+        B, T, A = x.shape
+        H, dk = m.aheads, A // m.aheads
+        Tp = _ceil64(T)
+        ctxs = []
+        kind = "lin" if m._linear_ffn else "conv"
+        for i in range(n_layers):
+            q = f"{pre}encoders.{i}."
+            c = dict(x0=x)
+            _, c["h1"] = ops.layer_norm(x, self.P(q + "norm1.weight"), self.P(q + "norm1.bias"))
+            wqkv = self._pack(("f", q + "qkv"), lambda: pack_dev(torch.cat([self.P(q + "self_attn.linear_q.weight"), self.P(q + "self_attn.linear_k.weight"),
+                                                                          self.P(q + "self_attn.linear_v.weight")], dim=1).t().contiguous()))
+            bqkv = torch.cat([self.P(q + "self_attn.linear_q.bias"), self.P(q + "self_attn.linear_k.bias"), self.P(q + "self_attn.linear_v.bias")])
+            _, qkv = ops.conv_gemm(c["h1"], wqkv, n=3 * A, k=A, bias=bqkv, out_f32=False, out_split=True)
+            c["qkv"] = qkv
+            ld = 3 * A
+            s_buf = torch.empty(B * H, T, Tp, dtype=torch.float32, device=x.device)
+            q_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=0, colh=dk)
+            k_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=A, colh=dk)
+            ops.batched_matmul_nt(qkv, qkv, batch=B, heads=H, m=T, n=T, k=dk, a_spec=q_spec, b_spec=k_spec, scale=1.0 / math.sqrt(dk),
+                                  y_f32=s_buf, y_batch_stride=H * T * Tp, y_head_stride=T * Tp, y_ld=Tp)
+            c["p"] = ops.masked_softmax(s_buf, key_lens, B, H, T, T)
+            vt = ops.transpose_heads(qkv, col0=2 * A, dk=dk, heads=H, ld_dst=Tp)
+            ctx = Split.empty((B, T, A), x.device)
+            p_spec = dict(rows=T, cols=Tp, ld=Tp, batch_stride=T * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
+            v_spec = dict(rows=dk, cols=Tp, ld=Tp, batch_stride=dk * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
+            ops.batched_matmul_nt(c["p"], vt, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=p_spec, b_spec=v_spec, y_split=ctx,
+                                  y_batch_stride=T * A, y_head_stride=dk, y_ld=A)
+            c["ctx"] = ctx
+            x1, _ = self.layer_fwd(ctx, q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin", residual=x)
+            c["x1"] = x1
+            _, c["h2"] = ops.layer_norm(x1, self.P(q + "norm2.weight"), self.P(q + "norm2.bias"))
+            _, c["u"] = self.layer_fwd(c["h2"], q + "feed_forward.w_1.weight", q + "feed_forward.w_1.bias", kind, act="relu", f32=False, split=True)
+            x, _ = self.layer_fwd(c["u"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind, residual=x1)
+            ctxs.append(c)
+        y, ys = ops.layer_norm(x, self.P(pre + "after_norm.weight"), self.P(pre + "after_norm.bias"), want_f32=True, want_split=True)
+        return y, ys, dict(layers=ctxs, x_last=x, pre=pre, n=n_layers)
+
+    def stack_bwd(self, dy, S):
+        """dy: gradient w.r.t. the after_norm output (fp32).  Returns the gradient w.r.t. the stack input."""
+        m = self.m
+        pre = S["pre"]
+        B, T, A = dy.shape
+        H, dk = m.aheads, A // m.aheads
+        Tp = _ceil64(T)
+        dev = dy.device
+        kind = "lin" if m._linear_ffn else "conv"
+        dx = torch.empty_like(dy)
+        ops.layer_norm_bwd(S["x_last"], self.P(pre + "after_norm.weight"), dy, dx, False, self.grads[pre + "after_norm.weight"],
+                           self.grads[pre + "after_norm.bias"])
+        for i in reversed(range(S["n"])):
+            q = f"{pre}encoders.{i}."
+            c = S["layers"][i]
+            # x2 = x1 + conv2(relu(conv1(LN2(x1))))
+            du = self.layer_bwd(dx, c["u"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind)
+            du_f, _ = ops.relu_bwd(du, c["u"], want_f32=True)
+            dh2 = self.layer_bwd(du_f, c["h2"], q + "feed_forward.w_1.weight", q + "feed_forward.w_1.bias", kind)
+            ops.layer_norm_bwd(c["x1"], self.P(q + "norm2.weight"), dh2, dx, True, self.grads[q + "norm2.weight"], self.grads[q + "norm2.bias"])
+            # x1 = x0 + out_proj(attention(LN1(x0)))
+            dctx = self.layer_bwd(dx, c["ctx"], q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin")
+            dctx_s = Split.from_f32(dctx)
+            qkv, p = c["qkv"], c["p"]
+            ld = 3 * A
+            dqkv = torch.zeros(B, T, ld, dtype=torch.float32, device=dev)
+            o_spec = dict(rows=T, cols=A, ld=A, batch_stride=T * A, batches=B, bmul=1, hmul=0, col0=0, colh=dk)
+            v_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=2 * A, colh=dk)
+            dp = torch.zeros(B * H, T, Tp, dtype=torch.float32, device=dev)
+            ops.batched_matmul_nt(dctx_s, qkv, batch=B, heads=H, m=T, n=T, k=dk, a_spec=o_spec, b_spec=v_spec, y_f32=dp,
+                                  y_batch_stride=H * T * Tp, y_head_stride=T * Tp, y_ld=Tp)                       # dP = dO V^T
+            ds = ops.softmax_bwd(p, dp, T, 1.0 / math.sqrt(dk))                                                  # includes the 1/sqrt(dk)
+            z_spec = dict(rows=T, cols=Tp, ld=Tp, batch_stride=T * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
+            d_spec = dict(rows=dk, cols=Tp, ld=Tp, batch_stride=dk * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
+
+            def t_sq(src):       # (B*H, T, Tp) -> transposed (B*H, T, Tp)
+                dst = Split.zeros((B * H, T, Tp), dev)
+                ops.transpose_planes(src, z=B * H, rows=T, src_zstride=T * Tp, ld_src=Tp, c0=0, cols=T, shift=0, r_out=T, dst=dst,
+                                     dst_zstride=T * Tp, ld_dst=Tp)
+                return dst
+
+            def t_heads(src, ld_src, col0):   # (B, T, ld_src)[.., col0 + h*dk + d] -> (B*H, dk, Tp)
+                dst = Split.zeros((B, H, dk, Tp), dev)
+                for h in range(H):
+                    ops.transpose_planes(src, z=B, rows=T, src_zstride=T * ld_src, ld_src=ld_src, c0=col0 + h * dk, cols=dk, shift=0,
+                                         r_out=T, dst=Split(dst.hi[:, h], dst.lo[:, h]), dst_zstride=H * dk * Tp, ld_dst=Tp)
+                return dst
+
+            pt, dot = t_sq(p), t_heads(dctx_s, A, 0)
+            ops.batched_matmul_nt(pt, dot, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=z_spec, b_spec=d_spec, y_f32=dqkv[:, :, 2 * A:],
+                                  y_batch_stride=T * ld, y_head_stride=dk, y_ld=ld)                               # dV = P^T dO
+            kt = t_heads(qkv, ld, A)
+            ops.batched_matmul_nt(ds, kt, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=z_spec, b_spec=d_spec, y_f32=dqkv,
+                                  y_batch_stride=T * ld, y_head_stride=dk, y_ld=ld)                               # dQ = dS K
+            dst_, qt = t_sq(ds), t_heads(qkv, ld, 0)
+            ops.batched_matmul_nt(dst_, qt, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=z_spec, b_spec=d_spec, y_f32=dqkv[:, :, A:],
+                                  y_batch_stride=T * ld, y_head_stride=dk, y_ld=ld)                               # dK = dS^T Q
+            # fused QKV projection: h1 [A] -> [3A]
+            dqs = Split.from_f32(dqkv)
+            bsum = torch.zeros(ld, dtype=torch.float32, device=dev)
+            ops.colsum_(dqkv.reshape(B * T, ld), bsum)
+            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                self.grads[q + "self_attn." + nm + ".bias"].copy_(bsum[j * A:(j + 1) * A])
+            wq_b = self._pack(("b", q + "qkv"), lambda: pack_dev(torch.cat([self.P(q + "self_attn.linear_q.weight"), self.P(q + "self_attn.linear_k.weight"),
+                                                                           self.P(q + "self_attn.linear_v.weight")], dim=1).contiguous()))
+            dh1, _ = ops.conv_gemm(dqs, wq_b, n=A, k=ld)
+            gw = torch.empty(A, ld, dtype=torch.float32, device=dev)
+            KK = B * Tp
+            xt = Split.zeros((A, KK), dev)
+            ops.transpose_planes(c["h1"], z=B, rows=T, src_zstride=T * A, ld_src=A, c0=0, cols=A, shift=0, r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KK)
+            dyt = Split.zeros((ld, KK), dev)
+            ops.transpose_planes(dqs, z=B, rows=T, src_zstride=T * ld, ld_src=ld, c0=0, cols=ld, shift=0, r_out=T, dst=dyt, dst_zstride=Tp, ld_dst=KK)
+            ops.batched_matmul_nt(xt, dyt, batch=1, heads=1, m=A, n=ld, k=KK,
+                                  a_spec=dict(rows=A, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0),
+                                  b_spec=dict(rows=ld, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0),
+                                  y_f32=gw, y_batch_stride=0, y_head_stride=0, y_ld=ld)
+            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                self.grads[q + "self_attn." + nm + ".weight"].copy_(gw[:, j * A:(j + 1) * A])
+            ops.layer_norm_bwd(c["x0"], self.P(q + "norm1.weight"), dh1, dx, True, self.grads[q + "norm1.weight"], self.grads[q + "norm1.bias"])
+        return dx
+
+    # ------------------------------------------------------------------------------------------------------------
+    # predictors
+    # ------------------------------------------------------------------------------------------------------------
+    def pred_fwd(self, pre, n_layers, hs_split):
+        saved, h = [], hs_split
+        for i in range(n_layers):
+            y, ys = self.layer_fwd(h, f"{pre}conv.{i}.0.weight", f"{pre}conv.{i}.0.bias", "conv", act="relu", f32=True, split=True)
+            _, hn = ops.layer_norm(y, self.P(f"{pre}conv.{i}.2.weight"), self.P(f"{pre}conv.{i}.2.bias"))
+            saved.append(dict(x=h, y=y, ys=ys))
+            h = hn
+        out, _ = self.layer_fwd(h, pre + "linear.weight", pre + "linear.bias", "lin")
+        return out, dict(layers=saved, h_last=h, pre=pre)
+
+    def pred_bwd(self, dout, S, need_dx=True):
+        pre = S["pre"]
+        g = self.layer_bwd(dout, S["h_last"], pre + "linear.weight", pre + "linear.bias", "lin")
+        n = len(S["layers"])
+        for i in reversed(range(n)):
+            c = S["layers"][i]
+            dy = torch.empty_like(g)
+            ops.layer_norm_bwd(c["y"], self.P(f"{pre}conv.{i}.2.weight"), g, dy, False, self.grads[f"{pre}conv.{i}.2.weight"],
+                               self.grads[f"{pre}conv.{i}.2.bias"])
+            dpre, _ = ops.relu_bwd(dy, c["ys"], want_f32=True)
+            g = self.layer_bwd(dpre, c["x"], f"{pre}conv.{i}.0.weight", f"{pre}conv.{i}.0.bias", "conv", need_dx=(i > 0 or need_dx))
+        return g
+
+    # ------------------------------------------------------------------------------------------------------------
+    # one training step
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_backward(self, batch):
+        m = self.m
+        L = _lib.lib()
+        st = _stream()
+        dev = m.device
+        self._packs = {}
+        self.gflat.zero_()
+        text = batch["text"].to(dev, torch.int64).contiguous()
+        B, T = text.shape
+        ilens = _i32(batch["text_lengths"].to(dev))
+        olens = _i32(batch["speech_lengths"].to(dev))
+        ds = batch["durations"].to(dev, torch.int64).contiguous()
+        ps = batch["pitch"].to(dev, torch.float32).reshape(B, T).contiguous()
+        es = batch["energy"].to(dev, torch.float32).reshape(B, T).contiguous()
+        ys = batch["speech"].to(dev, torch.float32).contiguous()
+        A, odim = m.adim, m.odim
+        # ---- forward (train mode) ----
+        x = ops.embed_pe(text, self.P("encoder.embed.0.weight"), None, self.P("encoder.embed.1.alpha"), None, m.padding_idx)
+        hs, hs_split, S_enc = self.stack_fwd(x, "encoder.", m.elayers, ilens)
+        p_raw, S_p = self.pred_fwd("pitch_predictor.", m.cfg["pitch"][0], hs_split)
+        e_raw, S_e = self.pred_fwd("energy_predictor.", m.cfg["energy"][0], hs_split)
+        d_raw, S_d = self.pred_fwd("duration_predictor.", m.cfg["dur"][0], hs_split)
+        p_outs = ops.mask_rows_(p_raw.reshape(B, T).clone(), ilens)
+        e_outs = ops.mask_rows_(e_raw.reshape(B, T).clone(), ilens)
+        d_outs = ops.mask_rows_(d_raw.reshape(B, T).clone(), ilens)
+        pe_w, ee_w = self.P("pitch_embed.0.weight"), self.P("energy_embed.0.weight")
+        hs2 = ops.variance_embed_add(hs, ps, es, pe_w.reshape(A, -1), self.P("pitch_embed.0.bias"), ee_w.reshape(A, -1),
+                                     self.P("energy_embed.0.bias"), None)
+        t_dec = ys.shape[1]
+        hs_lr, _ = ops.length_regulate(hs2, ds, t_dec)
+        xd = ops.embed_pe(None, None, hs_lr, self.P("decoder.embed.0.alpha"), None)
+        zs, zs_split, S_dec = self.stack_fwd(xd, "decoder.", m.dlayers, olens)
+        before, before_split = self.layer_fwd(zs_split, "feat_out.weight", "feat_out.bias", "lin", f32=True, split=True)
+        post, h = [], before_split
+        rows = B * t_dec
+        for i in range(m.postnet_layers):
+            last = i == m.postnet_layers - 1
+            cw = f"postnet.postnet.{i}.0.weight"
+            q = f"postnet.postnet.{i}.1."
+            conv_out, _ = self.layer_fwd(h, cw, None, "conv")
+            cdim = conv_out.shape[-1]
+            y = torch.empty_like(conv_out)
+            ysplit = Split.empty(tuple(conv_out.shape), dev) if not last else None
+            mean = torch.empty(cdim, device=dev)
+            rstd = torch.empty(cdim, device=dev)
+            _lib.check(L.pk_batch_norm_train(_ptr(conv_out), rows, cdim, _ptr(self.P(q + "weight")), _ptr(self.P(q + "bias")), 1e-5,
+                                             0 if last else 2, 0.9, _ptr(m._params[q + "_mean"]), _ptr(m._params[q + "_variance"]),
+                                             _ptr(self.sums), _ptr(y), _ptr(ysplit.hi) if ysplit else None,
+                                             _ptr(ysplit.lo) if ysplit else None, _ptr(mean), _ptr(rstd), st), "pk_batch_norm_train")
+            post.append(dict(x=h, conv=conv_out, y=y, mean=mean, rstd=rstd))
+            h = ysplit
+        after = before.clone()
+        ops.axpy_(1.0, post[-1]["y"], after)
+        # ---- loss and its gradient ----
+        losses = torch.empty(4, dtype=torch.float32, device=dev)
+        ws = torch.empty(12, dtype=torch.float32, device=dev)
+        _lib.check(L.pk_fs2_loss(_ptr(before), _ptr(after), _ptr(ys), _ptr(olens), t_dec, odim, _ptr(d_outs), _ptr(ds), _ptr(p_outs), _ptr(ps),
+                                 _ptr(e_outs), _ptr(es), _ptr(ilens), T, B, _ptr(ws), _ptr(losses), st), "pk_fs2_loss")
+        g_before, g_after = torch.empty_like(before), torch.empty_like(after)
+        g_d, g_p, g_e = torch.empty(B, T, 1, device=dev), torch.empty(B, T, 1, device=dev), torch.empty(B, T, 1, device=dev)
+        _lib.check(L.pk_fs2_loss_bwd(_ptr(before), _ptr(after), _ptr(ys), _ptr(olens), t_dec, odim, _ptr(d_outs), _ptr(ds), _ptr(p_outs),
+                                     _ptr(ps), _ptr(e_outs), _ptr(es), _ptr(ilens), T, B, _ptr(g_before), _ptr(g_after), _ptr(g_d), _ptr(g_p),
+                                     _ptr(g_e), st), "pk_fs2_loss_bwd")
+        # ---- backward ----
+        g = g_after                                            # after = before + postnet(before)
+        for i in reversed(range(m.postnet_layers)):
+            last = i == m.postnet_layers - 1
+            c = post[i]
+            q = f"postnet.postnet.{i}.1."
+            cdim = c["conv"].shape[-1]
+            dconv = torch.empty_like(c["conv"])
+            _lib.check(L.pk_batch_norm_bwd(_ptr(c["conv"]), _ptr(g), _ptr(c["y"]), _ptr(c["mean"]), _ptr(c["rstd"]), _ptr(self.P(q + "weight")),
+                                           0 if last else 2, rows, cdim, _ptr(self.sums), _ptr(dconv), st), "pk_batch_norm_bwd")
+            self.grads[q + "bias"].copy_(self.sums[:cdim])
+            self.grads[q + "weight"].copy_(self.sums[cdim:2 * cdim])
+            g = self.layer_bwd(dconv, c["x"], f"postnet.postnet.{i}.0.weight", None, "conv")
+        ops.axpy_(1.0, g_after, g)                             # residual path of `after`
+        ops.axpy_(1.0, g_before, g)                            # direct L1 on `before`
+        dzs = self.layer_bwd(g, zs_split, "feat_out.weight", "feat_out.bias", "lin")
+        dxd = self.stack_bwd(dzs, S_dec)
+        _lib.check(L.pk_embed_pe_bwd(None, _ptr(dxd), 0, 0, B, t_dec, A, None, _ptr(self.grads["decoder.embed.0.alpha"]), st), "pk_embed_pe_bwd")
+        dhs = torch.empty(B, T, A, dtype=torch.float32, device=dev)
+        _lib.check(L.pk_length_regulate_bwd(_ptr(dxd), _ptr(ds), B, T, A, t_dec, _ptr(dhs), st), "pk_length_regulate_bwd")
+        kp, ke = pe_w.shape[-1], ee_w.shape[-1]
+        _lib.check(L.pk_scalar_conv_wgrad(_ptr(dhs), _ptr(ps), B, T, A, kp, _ptr(self.grads["pitch_embed.0.weight"]),
+                                          _ptr(self.grads["pitch_embed.0.bias"]), st), "pk_scalar_conv_wgrad")
+        _lib.check(L.pk_scalar_conv_wgrad(_ptr(dhs), _ptr(es), B, T, A, ke, _ptr(self.grads["energy_embed.0.weight"]),
+                                          _ptr(self.grads["energy_embed.0.bias"]), st), "pk_scalar_conv_wgrad")
+        gd = self.pred_bwd(g_d, S_d)
+        ops.axpy_(1.0, gd, dhs)
+        ge = self.pred_bwd(g_e, S_e, need_dx=not self.sg_energy)
+        if not self.sg_energy:
+            ops.axpy_(1.0, ge, dhs)
+        gp = self.pred_bwd(g_p, S_p, need_dx=not self.sg_pitch)
+        if not self.sg_pitch:
+            ops.axpy_(1.0, gp, dhs)
+        dx = self.stack_bwd(dhs, S_enc)
+        _lib.check(L.pk_embed_pe_bwd(_ptr(text), _ptr(dx), m.idim, m.padding_idx, B, T, A, _ptr(self.grads["encoder.embed.0.weight"]),
+                                     _ptr(self.grads["encoder.embed.1.alpha"]), st), "pk_embed_pe_bwd")
+        return losses
+
+    def step(self, batch):
+        """One update: returns the four loss values (device tensor: l1, duration, pitch, energy)."""
+        losses = self.forward_backward(batch)
+        if self.world > 1:
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)      # the one exchange step of the path
+        self.step_count += 1
+        _lib.check(_lib.lib().pk_adam(_ptr(self.flat), _ptr(self.gflat), _ptr(self.adam_m), _ptr(self.adam_v), self.flat.numel(),
+                                      self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0 / self.world, _stream()), "pk_adam")
+        self.m._packed = None
+        return losses

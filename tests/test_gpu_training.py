@@ -1,0 +1,130 @@
+"""GPU parity of the FastSpeech2 training step (forward in train mode, loss, backward, Adam) against torch autograd on the
+oracle (FastSpeech2Updater.update_core, fastspeech2_updater.py:51-99)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, ref, rtol=2e-3, atol=2e-6):
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    return (a - ref).abs().max().item() <= rtol * ref.abs().max().item() + atol
+
+
+def test_train_kernels_unit(cuda):
+    """Row-wise backward kernels against torch autograd."""
+    from parakeet_b200 import _lib, ops
+    from parakeet_b200.ops import _ptr, _stream
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    # LayerNorm backward
+    x = torch.randn(37, 384, generator=g, requires_grad=True)
+    gam, bet = torch.randn(384, generator=g, requires_grad=True), torch.randn(384, generator=g, requires_grad=True)
+    dy = torch.randn(37, 384, generator=g)
+    torch.nn.functional.layer_norm(x, (384,), gam, bet).backward(dy)
+    dx = torch.zeros(37, 384, device=cuda)
+    dg, db = torch.zeros(384, device=cuda), torch.zeros(384, device=cuda)
+    ops.layer_norm_bwd(x.detach().to(cuda), gam.detach().to(cuda), dy.to(cuda), dx, False, dg, db)
+    assert _close(dx, x.grad) and _close(dg, gam.grad) and _close(db, bet.grad)
+    # softmax backward (with zero-probability padding columns)
+    s = torch.randn(6, 20, 64, generator=g)
+    s[:, :, 17:] = -1e30
+    s.requires_grad_(True)
+    p = torch.softmax(s, -1)
+    dp = torch.randn(6, 20, 64, generator=g)
+    (p * 0.3).backward(dp)        # scale 0.3 plays the role of 1/sqrt(dk)
+    ds = ops.softmax_bwd(ops.Split.from_f32(p.detach().to(cuda)), dp.to(cuda), 17, 0.3).float()
+    assert _close(ds[:, :, :17], s.grad[:, :, :17]) and ds[:, :, 17:].abs().max().item() == 0
+    # transpose with shift
+    a = torch.randn(3, 10, 16, generator=g)
+    src = ops.Split.from_f32(a.to(cuda))
+    dst = ops.Split.zeros((5, 3 * 64), cuda)
+    ops.transpose_planes(src, z=3, rows=10, src_zstride=160, ld_src=16, c0=4, cols=5, shift=-1, r_out=10, dst=dst, dst_zstride=64, ld_dst=192)
+    ref = torch.zeros(5, 3, 64)
+    ref[:, :, 1:10] = a[:, :9, 4:9].permute(2, 0, 1)
+    assert torch.allclose(dst.float().cpu().reshape(5, 3, 64), ref, atol=1e-4)
+    # BatchNorm train forward / backward (+ tanh)
+    xb = torch.randn(50, 24, generator=g, requires_grad=True)
+    gb, bb = torch.randn(24, generator=g, requires_grad=True), torch.randn(24, generator=g, requires_grad=True)
+    mean, var = xb.mean(0), xb.var(0, unbiased=False)
+    yb = torch.tanh((xb - mean) / torch.sqrt(var + 1e-5) * gb + bb)
+    dyb = torch.randn(50, 24, generator=g)
+    yb.backward(dyb)
+    rm, rv = torch.zeros(24, device=cuda), torch.ones(24, device=cuda)
+    sums = torch.zeros(64, device=cuda)
+    y = torch.empty(50, 24, device=cuda)
+    sm, sr = torch.empty(24, device=cuda), torch.empty(24, device=cuda)
+    xc = xb.detach().to(cuda)
+    _lib.check(L.pk_batch_norm_train(_ptr(xc), 50, 24, _ptr(gb.detach().to(cuda)), _ptr(bb.detach().to(cuda)), 1e-5, 2, 0.9, _ptr(rm), _ptr(rv),
+                                     _ptr(sums), _ptr(y), None, None, _ptr(sm), _ptr(sr), _stream()), "bn")
+    assert _close(y, yb) and _close(rm, 0.1 * mean) and _close(rv, 0.9 + 0.1 * var)
+    dxb = torch.empty(50, 24, device=cuda)
+    _lib.check(L.pk_batch_norm_bwd(_ptr(xc), _ptr(dyb.to(cuda)), _ptr(y), _ptr(sm), _ptr(sr), _ptr(gb.detach().to(cuda)), 2, 50, 24, _ptr(sums),
+                                   _ptr(dxb), _stream()), "bn_bwd")
+    assert _close(dxb, xb.grad) and _close(sums[:24], bb.grad) and _close(sums[24:48], gb.grad)
+    # length regulator backward
+    d = torch.tensor([[2, 0, 3], [1, 1, 1]])
+    dyl = torch.randn(2, 5, 8, generator=g)
+    dxl = torch.empty(2, 3, 8, device=cuda)
+    _lib.check(L.pk_length_regulate_bwd(_ptr(dyl.to(cuda)), _ptr(d.to(cuda)), 2, 3, 8, 5, _ptr(dxl), _stream()), "lr_bwd")
+    ref = torch.stack([torch.stack([dyl[0, 0:2].sum(0), torch.zeros(8), dyl[0, 2:5].sum(0)]), torch.stack([dyl[1, 0], dyl[1, 1], dyl[1, 2]])])
+    assert _close(dxl, ref)
+    # Adam, paddle semantics
+    from oracle import fastspeech2 as ofs
+    p0, g0 = torch.randn(1000, generator=g), torch.randn(1000, generator=g)
+    st = {}
+    ref1 = ofs.adam_step({"w": p0}, {"w": g0}, st, lr=1e-3)["w"]
+    ref2 = ofs.adam_step({"w": ref1}, {"w": g0 * 0.5}, st, lr=1e-3)["w"]
+    pc, mc, vc = p0.clone().to(cuda), torch.zeros(1000, device=cuda), torch.zeros(1000, device=cuda)
+    _lib.check(L.pk_adam(_ptr(pc), _ptr(g0.to(cuda)), _ptr(mc), _ptr(vc), 1000, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, _stream()), "adam")
+    assert torch.allclose(pc.cpu(), ref1, atol=1e-7)
+    _lib.check(L.pk_adam(_ptr(pc), _ptr((g0 * 0.5).to(cuda)), _ptr(mc), _ptr(vc), 1000, 1e-3, 0.9, 0.999, 1e-8, 2, 1.0, _stream()), "adam")
+    assert torch.allclose(pc.cpu(), ref2, atol=1e-7)
+
+
+def test_fs2_training_step_gradients_and_update(cuda):
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    params = ofs.synth_params(1)
+    batch = ofs.synth_train_batch(5, [9, 14, 11], dur_range=(1, 4))
+    losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
+    m.set_state_dict(params)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    losses = ts.forward_backward(batch)
+    got = [float(v) for v in losses]
+    ref = [losses_ref[k] for k in ("l1_loss", "duration_loss", "pitch_loss", "energy_loss")]
+    assert np.allclose(got, ref, rtol=1e-3), (got, ref)
+    bad = []
+    for k, gref in grads_ref.items():
+        if not _close(ts.grads[k], gref):
+            e = (ts.grads[k].cpu() - gref).abs().max().item()
+            bad.append((k, e, gref.abs().max().item()))
+    assert not bad, bad[:8]
+    for k, v in stats_ref.items():                       # BatchNorm running statistics (momentum 0.9)
+        assert _close(m.state_dict()[k], v), k
+    # one optimiser step (paddle Adam) moves every parameter like the oracle
+    ts2_ref = ofs.adam_step({k: params[k] for k in grads_ref}, grads_ref, {}, lr=1e-3)
+    ts.gflat  # gradients are in place from forward_backward
+    from parakeet_b200 import _lib
+    from parakeet_b200.ops import _ptr, _stream
+    _lib.check(_lib.lib().pk_adam(_ptr(ts.flat), _ptr(ts.gflat), _ptr(ts.adam_m), _ptr(ts.adam_v), ts.flat.numel(), 1e-3, 0.9, 0.999, 1e-8, 1,
+                                  1.0, _stream()), "pk_adam")
+    worst = max((m.state_dict()[k].cpu() - v).abs().max().item() for k, v in ts2_ref.items())
+    assert worst < 2e-4, worst     # first Adam step moves every weight by ~lr = 1e-3; sign flips of ~0 gradients stay below this
+
+
+def test_fs2_training_reduces_loss(cuda):
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
+    m.set_state_dict(ofs.synth_params(1))
+    batch = ofs.synth_train_batch(6, [12, 9, 15, 10], dur_range=(1, 4))
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    first = float(ts.step(batch).sum())
+    for _ in range(7):
+        last = float(ts.step(batch).sum())
+    assert last < first, (first, last)
