@@ -409,7 +409,7 @@ def train_step_grads(p, cfg, batch, stop_gradient_from_pitch_predictor=True, sto
     loss = l1 + dur + pitch + energy                                           # fastspeech2_updater.py:83
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in q.items() if not k.endswith(BUFFER_SUFFIXES)}
-    losses = dict(l1_loss=float(l1), duration_loss=float(dur), pitch_loss=float(pitch), energy_loss=float(energy), loss=float(loss))
+    losses = {k: float(v.detach()) for k, v in dict(l1_loss=l1, duration_loss=dur, pitch_loss=pitch, energy_loss=energy, loss=loss).items()}
     return losses, grads, new_stats
 
 
