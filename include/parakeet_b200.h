@@ -123,10 +123,12 @@ int pk_length_regulate(const float* x, const int64_t* dur, int32_t batch, int32_
  * scales: HOST int32 [n_stages].  Outputs (either may be NULL): c_f32 (batch, aux, T) channel-first fp32 and
  * c_hi/c_lo (batch, T, aux) channels-last split-bf16, T = frames * prod(scales).  frame_lens (device int32 [batch] or
  * NULL): valid frames per utterance of a ragged batch; each utterance is then upsampled exactly as if alone
- * (zero padding at its own end) and its samples past frame_lens[b]*hop are written as zero. */
+ * (zero padding at its own end) and its samples past frame_lens[b]*hop are written as zero.
+ * conv_in_ws: device fp32 workspace (batch, frames, aux) that receives the conv_in output (channels-last); aux % 8 == 0.
+ * Two launches: conv_in per frame, then the fused stretch/FIR cascade. */
 int pk_pwg_upsample(const float* mel, const float* conv_in_w, const float* fir, const int32_t* scales, int32_t n_stages,
-                    int32_t batch, int32_t aux, int32_t frames, int32_t window, const int32_t* frame_lens, float* c_f32,
-                    void* c_hi, void* c_lo, pk_stream_t stream);
+                    int32_t batch, int32_t aux, int32_t frames, int32_t window, const int32_t* frame_lens,
+                    float* conv_in_ws, float* c_f32, void* c_hi, void* c_lo, pk_stream_t stream);
 
 /* first_conv (:401-402, :464): x[b,t,r] = w[r] * noise[b,t] + bias[r] for 64 residual channels, written as split
  * planes (batch, t, 64); rows t >= lens[b] are written as zero (lens may be NULL). */
@@ -153,8 +155,8 @@ typedef struct pk_pwg_layer_args {
   const void* w1_lo;
   const void* w2_hi;
   const void* w2_lo;
-  const float* bias1;
-  const float* bias2;
+  const float* bias1;      /* HOST pointer [128]: conv bias (gate a | gate g); copied into the kernel parameter block */
+  const float* bias2;      /* HOST pointer [128]: conv1x1_skip bias (ignored, see pk_pwg_tail) | conv1x1_out bias */
   float* skip;             /* fp32 (batch, t, 64) running sum of skips */
   int32_t skip_init;       /* 1: overwrite (first layer), 0: accumulate */
   void* prof;              /* debug: NULL, or device uint64[64] phase-cycle counters accumulated by the kernel

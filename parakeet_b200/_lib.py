@@ -65,7 +65,7 @@ def _declare(L):
         "pk_conv_gemm_simt": [C.POINTER(ConvGemmArgs), vp],
         "pk_length_regulator_lens": [vp, i32, i32, vp, vp],
         "pk_length_regulate": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
-        "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
         "pk_pwg_first_conv": [vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
         "pk_pwg_tail": [vp, vp, vp, vp, vp, vp, f32, i64, vp, vp],

@@ -170,8 +170,10 @@ class PWGGenerator(Layer):
             w2 = torch.cat([p[pre + "conv1x1_skip.weight"][:, :, 0], p[pre + "conv1x1_out.weight"][:, :, 0]], dim=0)  # [128, 64]
             b1 = p.get(pre + "conv.bias", torch.zeros(128))
             b2 = torch.cat([p.get(pre + "conv1x1_skip.bias", zeros64), p.get(pre + "conv1x1_out.bias", zeros64)])
-            layers.append(dict(w1=_split_host(w1, dev), w2=_split_host(w2, dev), b1=b1.contiguous().to(dev),
-                               b2=b2.contiguous().to(dev), dil=2 ** (i % (self.layers // self.stacks))))
+            # the layer biases are HOST arrays: pk_pwg_residual_layer copies them into the kernel's parameter block
+            layers.append(dict(w1=_split_host(w1, dev), w2=_split_host(w2, dev),
+                               b1=np.ascontiguousarray(b1.numpy(), dtype=np.float32),
+                               b2=np.ascontiguousarray(b2.numpy(), dtype=np.float32), dil=2 ** (i % (self.layers // self.stacks))))
         pk["layers"] = layers
         pk["skip_bias_sum"] = torch.stack([p.get(f"conv_layers.{i}.conv1x1_skip.bias", zeros64) for i in range(self.layers)]).double().sum(0).float().contiguous().to(dev)
         pk["tail_w1"] = p["last_conv_layers.1.weight"][:, :, 0].contiguous().to(dev)
@@ -189,7 +191,8 @@ class PWGGenerator(Layer):
             dev = self.device
             ws = dict(xa=Split.zeros((B, T, 64), dev), xb=Split.zeros((B, T, 64), dev),
                       c=Split.empty((B, T, self.aux_channels), dev),
-                      skip=torch.empty(B, T, 64, dtype=torch.float32, device=dev))
+                      skip=torch.empty(B, T, 64, dtype=torch.float32, device=dev),
+                      conv_in=torch.empty(B, T // self.upsample_factor, self.aux_channels, dtype=torch.float32, device=dev))
             self._ws[key] = ws
         return ws
 
@@ -218,8 +221,8 @@ class PWGGenerator(Layer):
             frame_lens = torch.div(lens, self.upsample_factor, rounding_mode="floor").to(torch.int32)
         _lib.check(L.pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]), pk["fir_host"].ctypes.data_as(C.c_void_p),
                                      pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
-                                     self.aux_channels, frames, self.aux_context_window, _ptr(frame_lens), None,
-                                     _ptr(ws["c"].hi), _ptr(ws["c"].lo), st), "pk_pwg_upsample")
+                                     self.aux_channels, frames, self.aux_context_window, _ptr(frame_lens), _ptr(ws["conv_in"]),
+                                     None, _ptr(ws["c"].hi), _ptr(ws["c"].lo), st), "pk_pwg_upsample")
         _lib.check(L.pk_pwg_first_conv(_ptr(x), _ptr(pk["first_w"]), _ptr(pk["first_b"]), lens_p, B, T, _ptr(ws["xa"].hi),
                                        _ptr(ws["xa"].lo), st), "pk_pwg_first_conv")
         if lens is not None:
@@ -241,7 +244,7 @@ class PWGGenerator(Layer):
             args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
             args.w1_hi, args.w1_lo = lay["w1"].hi.data_ptr(), lay["w1"].lo.data_ptr()
             args.w2_hi, args.w2_lo = lay["w2"].hi.data_ptr(), lay["w2"].lo.data_ptr()
-            args.bias1, args.bias2 = lay["b1"].data_ptr(), lay["b2"].data_ptr()
+            args.bias1, args.bias2 = lay["b1"].ctypes.data, lay["b2"].ctypes.data
             args.skip_init = 1 if i == 0 else 0
             _lib.check(L.pk_pwg_residual_layer(C.byref(args), st), "pk_pwg_residual_layer")
             src, dst = dst, src
@@ -262,11 +265,12 @@ class PWGGenerator(Layer):
         frames = c.shape[-1] - 2 * self.aux_context_window
         out = torch.empty(B, self.aux_channels, frames * self.upsample_factor, dtype=torch.float32, device=self.device)
         c = c.contiguous().float()
+        cin = torch.empty(B, frames, self.aux_channels, dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib().pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]),
                                               pk["fir_host"].ctypes.data_as(C.c_void_p),
                                               pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
-                                              self.aux_channels, frames, self.aux_context_window, None, _ptr(out), None,
-                                              None, _stream()), "pk_pwg_upsample")
+                                              self.aux_channels, frames, self.aux_context_window, None, _ptr(cin), _ptr(out),
+                                              None, None, _stream()), "pk_pwg_upsample")
         return out
 
     def inference(self, c=None, x=None):
