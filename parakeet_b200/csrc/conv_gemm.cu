@@ -1,6 +1,7 @@
 // pk_conv_gemm: channels-last Conv1D / Linear / batched matmul as an im2col-free tiled GEMM on tcgen05.
 //
-//   - one CTA per 128(time) x BLOCK_N(channel) output tile, 192 threads:
+//   - persistent CTAs (one per SM) walking 128(time) x BLOCK_N(channel) output tiles, two TMEM accumulators so that the
+//     epilogue of tile i overlaps the main loop of tile i+1; 192 threads:
 //       warp 0   : TMA producer  (one elected lane)
 //       warp 1   : TMEM allocator + tcgen05.mma issuer (one elected lane)
 //       warps 2-5: epilogue (TMEM -> registers -> bias/act/residual/mask -> global), one output row per thread
@@ -31,7 +32,8 @@ struct GemmCfg {
 };
 
 struct GemmKernelArgs {
-  int m, n, k_chunks, taps, dil, pad, heads;
+  int m, n, k_chunks, taps, dil, pad, heads, batch;
+  int tiles_m, total_tiles;       // persistent schedule (set by launch<>)
   int a_bmul, a_hmul, a_col0, a_colh;
   int b_bmul, b_hmul, b_col0, b_colh, b_tap_stride;
   float scale;
@@ -47,6 +49,21 @@ struct GemmKernelArgs {
   int passes;
 };
 
+struct GemmTile {     // persistent tile schedule: m-tile fastest, then (batch, head), then n-tile, so that the CTAs
+  int m0, n0, bz, hz; // running at the same time share one n-tile of B (the weights stay hot in L2)
+};
+__device__ __forceinline__ GemmTile gemm_tile(int tile, int tiles_m, int zdim, int heads, int block_n) {
+  GemmTile t;
+  const int mt = tile % tiles_m;
+  const int r = tile / tiles_m;
+  const int z = r % zdim;
+  t.m0 = mt * kBlockM;
+  t.n0 = (r / zdim) * block_n;
+  t.bz = z / heads;
+  t.hz = z % heads;
+  return t;
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -58,16 +75,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* acc_full = empty_bar + Cfg::kStages;     // [2] MMA issuer -> epilogue: accumulator of tile i is complete
+  uint64_t* acc_empty = acc_full + 2;                // [2] epilogue -> MMA issuer: accumulator buffer drained
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBlockM;
-  const int n0 = blockIdx.y * BLOCK_N;
-  const int bz = blockIdx.z / p.heads;
-  const int hz = blockIdx.z % p.heads;
   const int num_chunks = p.taps * p.k_chunks;
+  const int zdim = p.batch * p.heads;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -78,10 +93,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_base_slot);
+  if (warp == 1) tmem_alloc<2 * Cfg::kTmemCols>(tmem_base_slot);   // two accumulators: epilogue(i) overlaps mainloop(i+1)
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -90,26 +108,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ TMA producer ------------------------------
-      const int a_batch = bz * p.a_bmul + hz * p.a_hmul;
-      const int b_batch = bz * p.b_bmul + hz * p.b_hmul;
-      const int a_col = p.a_col0 + hz * p.a_colh;
-      const int b_col = p.b_col0 + hz * p.b_colh;
       const uint32_t tx_bytes = (p.passes == 3) ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes);
-      for (int i = 0; i < num_chunks; ++i) {
-        const int s = i % Cfg::kStages;
-        const uint32_t ph = (i / Cfg::kStages) & 1;
-        const int tap = i / p.k_chunks;
-        const int kc = i % p.k_chunks;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-        const int a_row = m0 + (tap - p.pad) * p.dil;
-        tma_load_3d(st, &tm_a_hi, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
-        tma_load_3d(st + 2 * Cfg::kABytes, &tm_b_hi, &full_bar[s], b_col + tap * p.b_tap_stride + kc * kChunkK, n0, b_batch);
-        if (p.passes == 3) {
-          tma_load_3d(st + Cfg::kABytes, &tm_a_lo, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
-          tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s],
-                      b_col + tap * p.b_tap_stride + kc * kChunkK, n0, b_batch);
+      uint32_t it = 0;                                 // running stage counter across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const GemmTile t = gemm_tile(tile, p.tiles_m, zdim, p.heads, BLOCK_N);
+        const int a_batch = t.bz * p.a_bmul + t.hz * p.a_hmul;
+        const int b_batch = t.bz * p.b_bmul + t.hz * p.b_hmul;
+        const int a_col = p.a_col0 + t.hz * p.a_colh;
+        const int b_col = p.b_col0 + t.hz * p.b_colh;
+        for (int i = 0; i < num_chunks; ++i, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          const int tap = i / p.k_chunks;
+          const int kc = i % p.k_chunks;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          const int a_row = t.m0 + (tap - p.pad) * p.dil;
+          tma_load_3d(st, &tm_a_hi, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
+          tma_load_3d(st + 2 * Cfg::kABytes, &tm_b_hi, &full_bar[s], b_col + tap * p.b_tap_stride + kc * kChunkK, t.n0, b_batch);
+          if (p.passes == 3) {
+            tma_load_3d(st + Cfg::kABytes, &tm_a_lo, &full_bar[s], a_col + kc * kChunkK, a_row, a_batch);
+            tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[s],
+                        b_col + tap * p.b_tap_stride + kc * kChunkK, t.n0, b_batch);
+          }
         }
       }
     }
@@ -117,101 +139,135 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     if (lane == 0) {
       // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
-      for (int i = 0; i < num_chunks; ++i) {
-        const int s = i % Cfg::kStages;
-        const uint32_t ph = (i / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      int lt = 0;                                      // tiles processed by this CTA
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t a_hi = make_smem_desc_sw128(st);
-        const uint64_t a_lo = make_smem_desc_sw128(st + Cfg::kABytes);
-        const uint64_t b_hi = make_smem_desc_sw128(st + 2 * Cfg::kABytes);
-        const uint64_t b_lo = make_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+        const uint32_t d_tmem = tmem_base + buf * Cfg::kTmemCols;
+        for (int i = 0; i < num_chunks; ++i, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t a_hi = make_smem_desc_sw128(st);
+          const uint64_t a_lo = make_smem_desc_sw128(st + Cfg::kABytes);
+          const uint64_t b_hi = make_smem_desc_sw128(st + 2 * Cfg::kABytes);
+          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
 #pragma unroll
-        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
-          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // 32 B per K-step inside the 128B row
-          umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, (i | k) != 0);
-          if (p.passes == 3) {
-            umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
-            umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+          for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);  // 32 B per K-step inside the 128B row
+            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (i | k) != 0);
+            if (p.passes == 3) {
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
+        umma_commit(&acc_full[buf]);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;   // output time step
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const bool row_ok = row < p.m;
-    const bool row_live = row_ok && (p.lens == nullptr || row < p.lens[bz]);
-    const long long y_off = bz * p.y_batch_stride + hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const GemmTile t = gemm_tile(tile, p.tiles_m, zdim, p.heads, BLOCK_N);
+      const int buf = lt & 1;
+      const int row = t.m0 + quarter * 32 + lane;   // output time step
+      const bool row_ok = row < p.m;
+      const bool row_live = row_ok && (p.lens == nullptr || row < __ldg(p.lens + t.bz));
+      const long long y_off = t.bz * p.y_batch_stride + t.hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      __syncwarp();
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (row_ok && nb < p.n) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          float x = v[j] * p.scale;
-          if (p.bias != nullptr && n < p.n) x += __ldg(p.bias + n);
-          if (p.act == PK_ACT_RELU) x = fmaxf(x, 0.f);
-          else if (p.act == PK_ACT_TANH) x = tanhf(x);
-          v[j] = x;
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kTmemCols + c * 32, v);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {            // last read of this accumulator: hand it back to the MMA issuer
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[buf]);
         }
-        const bool full = (nb + 32 <= p.n) && ((p.y_ld & 7) == 0) && (((y_off + nb) & 7) == 0);
-        if (p.residual != nullptr) {
-          if (full) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + y_off + nb);
+        const int nb = t.n0 + c * 32;
+        if (row_ok && nb < p.n) {
+          // bias: one batch of independent loads per 32-column chunk (a dependent load per element would serialise the
+          // epilogue on global-memory latency), activation selected outside the element loops
+          float bv[32];
+          if (p.bias == nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+          } else if (nb + 32 <= p.n && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 r = __ldg(r4 + j);
-              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              const float4 b = __ldg(b4 + j);
+              bv[4 * j] = b.x; bv[4 * j + 1] = b.y; bv[4 * j + 2] = b.z; bv[4 * j + 3] = b.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.n) v[j] += __ldg(p.residual + y_off + nb + j);
+            for (int j = 0; j < 32; ++j) bv[j] = nb + j < p.n ? __ldg(p.bias + nb + j) : 0.f;
           }
-        }
-        if (!row_live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (full) {
-          if (p.y_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(p.y_f32 + y_off + nb);
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.scale, bv[j]);
+          if (p.act == PK_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == PK_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
           }
-          if (p.y_hi != nullptr) {
-            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + y_off + nb);
-            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + y_off + nb);
+          const bool full = (nb + 32 <= p.n) && ((p.y_ld & 7) == 0) && (((y_off + nb) & 7) == 0);
+          if (p.residual != nullptr) {
+            if (full) {
+              const float4* r4 = reinterpret_cast<const float4*>(p.residual + y_off + nb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 h, l;
-              split8(v + 8 * j, h, l);
-              oh[j] = h;
-              ol[j] = l;
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = __ldg(r4 + j);
+                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.n) v[j] += __ldg(p.residual + y_off + nb + j);
             }
           }
-        } else {
+          if (!row_live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j < p.n) {
-              if (p.y_f32 != nullptr) p.y_f32[y_off + nb + j] = v[j];
-              if (p.y_hi != nullptr) {
-                __nv_bfloat16 h, l;
-                split_bf16(v[j], h, l);
-                p.y_hi[y_off + nb + j] = h;
-                p.y_lo[y_off + nb + j] = l;
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (full) {
+            if (p.y_f32 != nullptr) {
+              float4* o4 = reinterpret_cast<float4*>(p.y_f32 + y_off + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.y_hi != nullptr) {
+              uint4* oh = reinterpret_cast<uint4*>(p.y_hi + y_off + nb);
+              uint4* ol = reinterpret_cast<uint4*>(p.y_lo + y_off + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 h, l;
+                split8(v + 8 * j, h, l);
+                oh[j] = h;
+                ol[j] = l;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (nb + j < p.n) {
+                if (p.y_f32 != nullptr) p.y_f32[y_off + nb + j] = v[j];
+                if (p.y_hi != nullptr) {
+                  __nv_bfloat16 h, l;
+                  split_bf16(v[j], h, l);
+                  p.y_hi[y_off + nb + j] = h;
+                  p.y_lo[y_off + nb + j] = l;
+                }
               }
             }
           }
@@ -223,7 +279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<2 * Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -291,14 +347,13 @@ static int validate(const pk_conv_gemm_args* a) {
   PK_CHECK_ARG((a->y_f32 != nullptr) || (a->y_hi != nullptr), "no output requested");
   PK_CHECK_ARG((a->y_hi == nullptr) == (a->y_lo == nullptr), "y_hi and y_lo must both be set or both NULL");
   PK_CHECK_ARG(a->act >= PK_ACT_NONE && a->act <= PK_ACT_TANH, "unknown activation %d", a->act);
-  PK_CHECK_ARG(static_cast<long long>(a->batch) * a->heads <= 65535, "batch*heads exceeds grid.z limit");
   return PK_OK;
 }
 
 static GemmKernelArgs to_kernel_args(const pk_conv_gemm_args* a) {
   GemmKernelArgs p;
   p.m = a->m; p.n = a->n; p.k_chunks = (a->k + kChunkK - 1) / kChunkK; p.taps = a->taps; p.dil = a->dil; p.pad = a->pad;
-  p.heads = a->heads;
+  p.heads = a->heads; p.batch = a->batch; p.tiles_m = 0; p.total_tiles = 0;
   p.a_bmul = a->a.bmul; p.a_hmul = a->a.hmul; p.a_col0 = a->a.col0; p.a_colh = a->a.colh;
   p.b_bmul = a->b.bmul; p.b_hmul = a->b.hmul; p.b_col0 = a->b.col0; p.b_colh = a->b.colh;
   p.b_tap_stride = p.k_chunks * kChunkK;
@@ -328,8 +383,12 @@ static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
     PK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const GemmKernelArgs p = to_kernel_args(a);
-  dim3 grid((a->m + kBlockM - 1) / kBlockM, (a->n + BLOCK_N - 1) / BLOCK_N, a->batch * a->heads);
+  GemmKernelArgs p = to_kernel_args(a);
+  p.tiles_m = (a->m + kBlockM - 1) / kBlockM;
+  const long long total = static_cast<long long>(p.tiles_m) * ((a->n + BLOCK_N - 1) / BLOCK_N) * a->batch * a->heads;
+  PK_CHECK_ARG(total < (1LL << 31), "too many output tiles");
+  p.total_tiles = static_cast<int>(total);
+  const int grid = static_cast<int>(std::min<long long>(total, sm_count()));   // persistent: one CTA per SM
   conv_gemm_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   PK_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -1,0 +1,56 @@
+"""CUDA-graph replay for the launch-bound inference paths (FastSpeech2: ~120 launches of 10-100 us; WaveFlow: 5 040
+launches per call).  The reference has no counterpart (Paddle dygraph launches op by op); SURVEY 8(d) asks for CUDA
+events around the captured graph.
+
+`GraphRunner.run(key, fn, inputs)` runs `fn(*inputs)` eagerly the first time a key is seen (that call is also the
+warm-up that packs weights and sets kernel attributes), captures it into a CUDA graph the second time, and replays the
+graph afterwards: inputs are copied into the graph's static input tensors, outputs are the graph's static output tensors
+(valid until the next replay of the same key - callers clone what they hand out).  `fn` must not synchronise with the
+host.  Set PK_CUDA_GRAPHS=0 to run everything eagerly.
+"""
+import os
+
+import torch
+
+
+def _tensors(obj):
+    if isinstance(obj, torch.Tensor):
+        return [obj]
+    if isinstance(obj, (tuple, list)):
+        return [t for o in obj for t in _tensors(o)]
+    return []
+
+
+class GraphRunner:
+    def __init__(self, max_graphs=32):
+        self.enabled = os.environ.get("PK_CUDA_GRAPHS", "1") != "0"
+        self.max_graphs = max_graphs
+        self._seen = set()
+        self._graphs = {}
+        self.replays = 0
+
+    def run(self, key, fn, inputs):
+        if not self.enabled:
+            return fn(*inputs)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if key not in self._seen or len(self._graphs) >= self.max_graphs:
+                self._seen.add(key)
+                return fn(*inputs)
+            static_in = [t.clone() for t in inputs]
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn(*static_in)
+            ent = (graph, static_in, out)
+            self._graphs[key] = ent
+        graph, static_in, out = ent
+        for s, t in zip(static_in, inputs):
+            s.copy_(t)
+        graph.replay()
+        self.replays += 1
+        return out
+
+    def clear(self):
+        self._graphs.clear()
+        self._seen.clear()

@@ -10,13 +10,26 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
+from .graph import GraphRunner
+
 
 class Layer:
     def __init__(self, device=None):
         self._params = OrderedDict()
+        self._graphs = GraphRunner() # CUDA graphs of the inference paths; they bake the packed weights' addresses
         self._packed = None          # derived kernel-ready weights (built on first forward)
         self.training = True
         self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+
+    @property
+    def _packed(self):
+        return self.__dict__.get("_packed_value")
+
+    @_packed.setter
+    def _packed(self, value):
+        self.__dict__["_packed_value"] = value
+        if value is None and "_graphs" in self.__dict__:
+            self._graphs.clear()     # captured graphs point at the old packed weights
 
     # -- parameter registry ----------------------------------------------------------------------------------
     def _register(self, name, tensor):

@@ -331,15 +331,14 @@ class FastSpeech2(Layer):
     # ------------------------------------------------------------------------------------------------------------
     # _forward (reference fastspeech2.py:377-466)
     # ------------------------------------------------------------------------------------------------------------
-    def _forward(self, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False):
-        if not xs.is_cuda:
-            raise _lib.PkError("FastSpeech2 needs CUDA tensors (no CPU fallback)")
+    def _stage_a(self, xs, ilens32, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False):
+        """Encoder, variance predictors, duration rounding, variance embeddings, frame counts: everything whose shapes
+        depend on (B, T) only.  No host synchronisation (CUDA-graph capturable)."""
         pk = self._pack()
         B, T = xs.shape
-        ilens32 = _i32(ilens.to(xs.device))
         row_lens = ilens32 if independent else None
         # encoder: Embedding(padding_idx=0) + ScaledPositionalEncoding, FFT blocks, after_norm; keys masked by ilens
-        x = ops.embed_pe(xs.to(torch.int64), pk["emb"], None, pk["enc_alpha"], row_lens, self.padding_idx)
+        x = ops.embed_pe(xs, pk["emb"], None, pk["enc_alpha"], row_lens, self.padding_idx)
         hs, hs_split = self._encoder_stack(x, pk["enc"], pk["enc_norm"], row_lens, ilens32, want_split_out=True)
         # variance predictors (masked_fill with the pad mask, variance_predictor.py:101-103)
         p_outs = ops.mask_rows_(self._predictor(pk["pitch"], hs_split, row_lens), ilens32)
@@ -357,26 +356,61 @@ class FastSpeech2(Layer):
             hs2 = ops.variance_embed_add(hs, ps.reshape(B, T).float(), es.reshape(B, T).float(), pk["pe_w"], pk["pe_b"],
                                          pk["ee_w"], pk["ee_b"], row_lens)
             d_int = ds.to(torch.int64)
-        # length regulator: device-side frame counts, one D2H copy of B integers to size the decoder
+        # length regulator: device-side frame counts
         lr_lens = ops.length_regulator_lens(d_int)
-        t_dec = int(lr_lens.max().item())
-        if t_dec == 0:
-            empty = torch.zeros(B, 0, self.odim, device=xs.device)
-            return empty, empty, d_outs, p_outs, e_outs, lr_lens
+        return hs2, d_int, lr_lens, d_outs, p_outs, e_outs
+
+    def _stage_b(self, hs2, d_int, t_dec, dec_rows, dec_keys):
+        """Length regulator, decoder, feat_out, postnet for a decoder length t_dec known on the host (capturable)."""
+        pk = self._pack()
         hs_lr, _ = ops.length_regulate(hs2, d_int, t_dec)
-        if independent:
-            dec_rows, dec_keys = lr_lens, lr_lens
-        elif olens is not None and not is_inference:
-            dec_rows, dec_keys = None, _i32(olens.to(xs.device))   # h_masks = _source_mask(olens)  (:451)
-        else:
-            dec_rows, dec_keys = None, None                        # h_masks = None                 (:453)
         x = ops.embed_pe(None, None, hs_lr, pk["dec_alpha"], dec_rows)
         _, zs = self._encoder_stack(x, pk["dec"], pk["dec_norm"], dec_rows, dec_keys, want_split_out=True)
         zs_split = zs if isinstance(zs, Split) else None
         before, before_split = ops.conv_gemm(zs_split, pk["feat_w"], n=self.odim, k=self.adim, bias=pk["feat_b"], lens=dec_rows,
                                              out_f32=True, out_split=True)
         after = before if self.postnet_layers == 0 else self._postnet(before, before_split, dec_rows)
+        return before, after
+
+    def _forward(self, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False):
+        if not xs.is_cuda:
+            raise _lib.PkError("FastSpeech2 needs CUDA tensors (no CPU fallback)")
+        B = xs.shape[0]
+        ilens32 = _i32(ilens.to(xs.device))
+        hs2, d_int, lr_lens, d_outs, p_outs, e_outs = self._stage_a(xs.to(torch.int64), ilens32, ds, ps, es, is_inference, alpha,
+                                                                    independent)
+        t_dec = int(lr_lens.max().item())        # the one D2H copy (B integers) that sizes the decoder
+        if t_dec == 0:
+            empty = torch.zeros(B, 0, self.odim, device=xs.device)
+            return empty, empty, d_outs, p_outs, e_outs, lr_lens
+        if independent:
+            dec_rows, dec_keys = lr_lens, lr_lens
+        elif olens is not None and not is_inference:
+            dec_rows, dec_keys = None, _i32(olens.to(xs.device))   # h_masks = _source_mask(olens)  (:451)
+        else:
+            dec_rows, dec_keys = None, None                        # h_masks = None                 (:453)
+        before, after = self._stage_b(hs2, d_int, t_dec, dec_rows, dec_keys)
         return before, after, d_outs, p_outs, e_outs, lr_lens
+
+    def _infer(self, xs, ilens, alpha=1.0):
+        """Inference through CUDA graphs (parakeet_b200/graph.py): every utterance is computed as if alone (utterance-local
+        padding and key masks), so the decoder length can be rounded up to a bucket of 32 frames - padded rows are inert
+        and are sliced off - and the two shape-static halves replay as graphs.  Returns (after, d_outs, frame counts)."""
+        if not xs.is_cuda:
+            raise _lib.PkError("FastSpeech2 needs CUDA tensors (no CPU fallback)")
+        B, T = xs.shape
+        xs = xs.to(torch.int64).contiguous()
+        ilens32 = _i32(ilens.to(xs.device))
+        alpha = float(alpha)
+        fa = lambda x_, l_: self._stage_a(x_, l_, is_inference=True, alpha=alpha, independent=True)
+        hs2, d_int, lr_lens, d_outs, _, _ = self._graphs.run(("a", B, T, alpha), fa, [xs, ilens32])
+        t_dec = int(lr_lens.max().item())
+        if t_dec == 0:
+            return torch.zeros(B, 0, self.odim, device=xs.device), d_outs.clone(), lr_lens.clone()
+        bucket = (t_dec + 31) // 32 * 32
+        fb = lambda h_, d_, l_: self._stage_b(h_, d_, bucket, l_, l_)
+        _, after = self._graphs.run(("b", B, T, bucket), fb, [hs2, d_int, lr_lens])
+        return after[:, :t_dec].clone(), d_outs.clone(), lr_lens.clone()
 
     # ------------------------------------------------------------------------------------------------------------
     # public API (reference :289-375, :468-558)
@@ -400,15 +434,14 @@ class FastSpeech2(Layer):
             _, outs, *_ = self._forward(xs, ilens, None, durations.to(torch.int64).unsqueeze(0), pitch.unsqueeze(0),
                                         energy.unsqueeze(0), is_inference=False)
         else:
-            _, outs, *_ = self._forward(xs, ilens, is_inference=True, alpha=alpha)
+            outs, _, _ = self._infer(xs, ilens, alpha)
         return outs[0]
 
     def batch_inference(self, text, text_lengths, alpha: float = 1.0):
         """Batched form of `inference`: padded ids (B, Tmax) + lengths -> (mel (B, Lmax, odim), frame counts (B,) int32,
         durations (B, Tmax)).  Each utterance is computed exactly as if it had been passed to `inference` alone
         (utterance-local zero padding and key masking); rows past an utterance's own length are zero."""
-        _, after, d_outs, _, _, olens = self._forward(text.to(torch.int64), text_lengths, is_inference=True, alpha=alpha,
-                                                      independent=True)
+        after, d_outs, olens = self._infer(text, text_lengths, alpha)
         return after, olens, d_outs
 
 

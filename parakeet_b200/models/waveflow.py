@@ -107,6 +107,7 @@ class ConditionalWaveFlow(Layer):
                                     in_b=p[pre + "input_proj.bias"].to(dev), layers=layers,
                                     out_w=p[pre + "output_proj.weight"].reshape(2, C).contiguous().to(dev),
                                     out_b=p[pre + "output_proj.bias"].to(dev)))
+        pk["perms"] = [torch.tensor(pm, dtype=torch.int64, device=dev) for pm in self.perms]   # device-side gather indices
         self._packed = pk
         return pk
 
@@ -147,7 +148,7 @@ class ConditionalWaveFlow(Layer):
         rows = B * W
         for fi in reversed(range(self.n_flows)):
             perm = self.perms[fi]
-            z = z[:, perm, :].contiguous()                                                # geo.shuffle_dim(z, 2, perm)
+            z = z.index_select(1, pk["perms"][fi])                                        # geo.shuffle_dim(z, 2, perm)
             cmap = [cmap[j] for j in perm]
             fw = pk["flows"][fi]
             x = torch.empty_like(z)
@@ -179,10 +180,17 @@ class ConditionalWaveFlow(Layer):
         """reference :784-805; the noise z (B, T_c) may be supplied (parity tests), else torch.randn."""
         if not mel.is_cuda:
             raise _lib.PkError("ConditionalWaveFlow needs CUDA tensors (no CPU fallback)")
-        condition = self.encode(mel, trim_conv_artifact=True)
+        mel = mel.contiguous().float()
+        B, _, frames = mel.shape
+        t_c = frames
+        for f in self.upsample_factors:                                     # each transposed conv trims f samples (:121-126)
+            t_c = t_c * f - f
         if z is None:
-            z = torch.randn(condition.shape[0], condition.shape[-1], device=mel.device)
-        return self.inverse(z, condition)
+            z = torch.randn(B, t_c, device=mel.device)
+        assert z.shape == (B, t_c), (tuple(z.shape), (B, t_c))
+        # one CUDA graph per (B, frames): the 5 040 small launches of the row-by-row inverse replay without host work
+        fn = lambda m_, z_: self.inverse(z_, self.encode(m_, trim_conv_artifact=True))
+        return self._graphs.run(("infer", B, frames), fn, [mel, z.contiguous().float()]).clone()
 
     def predict(self, mel):
         """reference :807-825: numpy mel (n_mels, T') -> numpy audio."""

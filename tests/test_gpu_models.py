@@ -201,3 +201,45 @@ def test_fs2_loss_vs_oracle(cuda, fs2):
                                           b["text_lengths"], olens)
     got = [float(v) for v in losses]
     assert np.allclose(got, g["losses"], rtol=1e-3), (got, g["losses"])
+
+
+def test_cuda_graph_replay_matches_eager(cuda, fs2):
+    """The launch-bound inference paths replay as CUDA graphs from their third call on (parakeet_b200/graph.py): the
+    replays must reproduce the eager result bit for bit, for new inputs of the same shape, and a weight update must drop
+    the captured graphs."""
+    from oracle import fastspeech2 as ofs
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    m, params = fs2
+    lengths = [50, 77, 64]
+    outs = []
+    for seed in (11, 12, 13, 11):                                   # eager, capture, replay, replay with the first inputs
+        xs, il = ofs.synth_text(seed, lengths)
+        mel, olens, d = m.batch_inference(xs.to(cuda), il.to(cuda))
+        outs.append((mel.clone(), olens.clone(), d.clone()))
+    assert m._graphs.replays >= 2
+    assert torch.equal(outs[0][0], outs[3][0]) and torch.equal(outs[0][1], outs[3][1]) and torch.equal(outs[0][2], outs[3][2])
+    xs, il = ofs.synth_text(13, lengths)
+    for i, n in enumerate(lengths):                                 # a replayed result against the oracle
+        with torch.no_grad():
+            r = ofs.fs2_inference(params, None, xs[i, :n])
+        L = int(outs[2][1][i])
+        assert L == r.shape[0] and rel_err(outs[2][0][i, :L], r) < TOL
+    n_graphs = len(m._graphs._graphs)
+    assert n_graphs >= 1
+    m.set_state_dict(m.state_dict())                                # invalidates the packed weights -> graphs dropped
+    assert len(m._graphs._graphs) == 0
+
+    wf = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    wp = owf.synth_params(4)
+    wf.set_state_dict(wp)
+    g = torch.Generator().manual_seed(5)
+    res = []
+    for it in range(3):
+        mel = torch.randn(2, 80, 6, generator=g) * 0.5 - 3
+        z = torch.randn(2, 256 * 6 - 272, generator=g)
+        res.append((mel, z, wf.infer(mel.to(cuda), z=z.to(cuda))))
+    assert wf._graphs.replays >= 1
+    with torch.no_grad():
+        ref = owf.infer(owf.fold_weight_norm(wp), res[2][0], res[2][1])
+    assert rel_err(res[2][2], ref) < TOL
