@@ -242,14 +242,14 @@ def main():
     layer_launch_ms = sum(layer_ms) / max(len(layer_ms), 1) / 30.0            # average residual-layer kernel duration
     flops_per_launch = FLOP_PER_SAMPLE_LAYER * samples_per_step               # algorithmic (one pass), 330 GFLOP
     achieved_tf = flops_per_launch / (layer_launch_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "pk::pwg_layer_kernel", "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"],
+    roofline = {"bound": "tensor", "kernel": "pk::pwg_layer_pair_kernel", "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact config (B=32, 400 frames), from
-                # `ncu --set full` (profiles/r01_pwg_layer_final_b32_ncu.txt); algorithmic bytes are 5.16e9
-                "traffic": 5.169e9, "traffic_unit": "bytes/launch",
+                # `ncu --set full` (profiles/r01_pwg_layer_pair_b32_ncu.txt); algorithmic bytes are 5.16e9
+                "traffic": 5.122e9, "traffic_unit": "bytes/launch",
                 "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launch_ms": layer_launch_ms, "launches_per_step": 30,
-                "note": "algorithmic FLOPs; split-bf16 operands execute 3 tensor-core passes per product",
+                "note": "algorithmic FLOPs; split-bf16 operands execute 3 tensor-core passes per product (+ the residual pass)",
                 "hbm_algorithmic_gbs": (samples_per_step * (256 + 256 + 512 + 320)) / (layer_launch_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": pk["hbm_gbs"]}
 

@@ -504,6 +504,9 @@ pwg_layer_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_const
 //     its MMA thread waits on: full[s] (TMA bytes of BOTH CTAs), acc1_empty, z_full, acc2_empty (warp-elected remote arrivals)
 //   both CTAs: TMA producer (own rows), gate warps (own TMEM lanes), store warps; local barriers empty[s], acc1_full,
 //     acc2_full (multicast commits), g2_free (producer -> gate warps)
+//   Only z_full is waited on with cluster-scope acquire (it publishes generic-proxy smem writes of the peer CTA); every
+//   other barrier orders tensor-core / TMA / TMEM traffic only, and a cluster-scope acquire would cost an L1 invalidate
+//   (CCTL.IVALL) per wait on the MMA issuer's critical path.
 constexpr int kP2Stages = 3;
 constexpr int kP2StageBytes = 2 * kPwgTile;                  // A hi, A lo
 constexpr int kP2WTile = 64 * kSwizzleBytes;                 // 8 KB: 64 output channels x one K-chunk of one plane
@@ -617,7 +620,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
         for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
           const int s = it % kP2Stages;
           PK_TICK(1)
-          mbar_wait_cluster_a(empty_bar + 8 * s, ((it / kP2Stages) & 1) ^ 1);
+          mbar_wait_a(empty_bar + 8 * s, ((it / kP2Stages) & 1) ^ 1);
           PK_TICK(0)
           const uint32_t st = smem + s * kP2StageBytes;
           const uint32_t fb = full_leader + 8 * s;
@@ -637,7 +640,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
       auto load_g2 = [&]() {
         const int s = it % kP2Stages;
         PK_TICK(1)
-        mbar_wait_cluster_a(empty_bar + 8 * s, ((it / kP2Stages) & 1) ^ 1);
+        mbar_wait_a(empty_bar + 8 * s, ((it / kP2Stages) & 1) ^ 1);
         PK_TICK(0)
         mbar_arrive_a(g2_free + 8 * (n_g2 & 1));   // own gate warps may write z of this tile into the stage
         ++n_g2;
@@ -678,14 +681,14 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
       auto g1 = [&](int i) {
         const int buf = i & 1;
         PK_TICK(6)
-        mbar_wait_cluster_a(acc1_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+        mbar_wait_a(acc1_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
         PK_TICK(0)
         tcgen05_fence_after();
         const uint32_t d = tmem_base + buf * 128;
         for (int j = 0; j < kPwgG1Chunks; ++j, ++it) {
           const int s = it % kP2Stages;
           PK_TICK(2)
-          mbar_wait_cluster_a(full_bar + 8 * s, (it / kP2Stages) & 1);
+          mbar_wait_a(full_bar + 8 * s, (it / kP2Stages) & 1);
           PK_TICK(1)
           tcgen05_fence_after();
           const int wj = j == 0 ? 0 : j == 1 ? 2 : j == 2 ? 3 : j == 3 ? 4 : 1;
@@ -694,7 +697,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
           if (j == kPwgG1Chunks - 1) {
             // residual pass: acc2(i) = [0 | x_hi + x_lo] from the centre-tap tiles of both CTAs
             PK_TICK(2)
-            mbar_wait_cluster_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+            mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
             PK_TICK(4)
             tcgen05_fence_after();
             const uint64_t a_hi = make_smem_desc_sw128(st), a_lo = make_smem_desc_sw128(st + kPwgTile);
@@ -716,7 +719,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
         PK_TICK(2)
         mbar_wait_cluster_a(z_full + 8 * (i & 1), (i >> 1) & 1);   // the gate warps of both CTAs wrote z into stage s
         PK_TICK(3)
-        mbar_wait_cluster_a(full_bar + 8 * s, (it / kP2Stages) & 1);
+        mbar_wait_a(full_bar + 8 * s, (it / kP2Stages) & 1);
         PK_TICK(5)
         tcgen05_fence_after();
         mma_chunk(tmem_base + 256 + buf * 128, smem + s * kP2StageBytes, w2, 4, false);
@@ -762,7 +765,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
       ++it;
       const int buf = i & 1;
       PK_TICK(6)
-      mbar_wait_cluster_a(acc1_full + 8 * buf, (i >> 1) & 1);
+      mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
       PK_TICK(0)
       tcgen05_fence_after();
       uint32_t zh[32], zl[32];
@@ -827,7 +830,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
         const int tt = m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
         float* dst = p.skip + (static_cast<long long>(b) * p.t + tt) * 64;
         PK_TICK(6)
-        mbar_wait_cluster_a(acc2_full + 8 * buf, (i >> 1) & 1);
+        mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
         PK_TICK(0)
         tcgen05_fence_after();
 #pragma unroll
@@ -868,7 +871,7 @@ pwg_layer_pair_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_
         const long long row_off = (static_cast<long long>(b) * p.t + trow) * 64;
         const bool live = trow < len;
         PK_TICK(6)
-        mbar_wait_cluster_a(acc2_full + 8 * buf, (i >> 1) & 1);
+        mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
         PK_TICK(0)
         tcgen05_fence_after();
 #pragma unroll
