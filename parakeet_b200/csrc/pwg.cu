@@ -4,9 +4,11 @@
 //        GEMM1  h[128 t x 128]  = sum_{tap} x[t + (tap-1) d, 0:64] W_conv[tap] + c[t, 0:80] W_aux      (K = 272)
 //        gate   z[128 x 64]     = tanh(h[:, :64] + b) * sigmoid(h[:, 64:] + b)       (TMEM -> regs -> smem, never HBM)
 //        GEMM2  [skip | out]    = z W_so                                              (K = 64)
-//        epi    skip_acc += skip + b_skip ;  x_out = (out + b_out + x) * sqrt(0.5)
-//     persistent CTAs (one per SM), 10 warps: TMA producer, MMA issuer, 8 epilogue warps; double-buffered TMEM
-//     accumulators so GEMM1 of tile i+1 overlaps the gate/epilogue of tile i.
+//        epi    skip_acc += skip (its bias is summed into the tail);  x_out = (out + b_out + x) * sqrt(0.5), where +x is a
+//               tensor-core pass x [0 | I] into the GEMM2 accumulator
+//     persistent CTAs, 16 warps: TMA producer, MMA issuer, 4 gate warps, 8 store warps; double-buffered TMEM accumulators so
+//     GEMM1 of tile i+1 overlaps the gate / stores of tile i.  Two variants: pwg_layer_pair_kernel (CTA pairs, cta_group::2,
+//     weights resident in shared memory; default) and pwg_layer_kernel (one CTA per SM, weights streamed per tile).
 //   pk_pwg_upsample       : ConvInUpsampleNet (:201-216) conv_in + [nearest stretch + FIR] x scales, fused per frame.
 //   pk_pwg_first_conv     : first_conv 1 -> R channels (:464).
 //   pk_pwg_tail           : skips * sqrt(1/L) -> ReLU -> 1x1 -> ReLU -> 1x1 (:469-471).
@@ -23,14 +25,14 @@ namespace pk {
 // ---------------------------------------------------------------------------------------------------------------
 // fused residual layer
 // ---------------------------------------------------------------------------------------------------------------
-// Warp roles (18 warps, 1 CTA per SM, persistent over 128-sample tiles):
+// Warp roles (16 warps, 1 CTA per SM, persistent over 128-sample tiles):
 //   warp 0      TMA producer   : per tile 5 K-chunks for GEMM1 (3 dilated taps of x, 2 chunks of c; A and B = 64 KB
 //                                per stage) + 1 chunk for GEMM2 (W2 only; the A half of that stage receives z)
 //   warp 1      MMA issuer     : G1(0); then per tile { G1(i+1); G2(i) } so GEMM1 of the next tile overlaps the gate
 //   warps 4-7   gate  warps    : acc1 (TMEM) -> tanh * sigmoid -> split-bf16 z tile written (128B-swizzled) into the
 //                                A half of the pipeline stage reserved for GEMM2
-//   warps 8-15  store warps    : acc2 (TMEM) -> + bias -> per-warp 32x32 transpose in smem -> coalesced
-//                                red.global.add (skip sum) / residual + split planes (x_out)
+//   warps 8-15  store warps    : acc2 (TMEM) -> skip half: red.global.add.v4 into the fp32 skip sum; out half: + bias,
+//                                * sqrt(1/2), split planes with 256-bit stores (row per thread)
 // TMEM: acc1[2] at columns 0/128, acc2[2] at 256/384 (fp32 128x128 each).
 constexpr int kPwgR = 64;        // residual channels
 constexpr int kPwgG = 128;       // gate channels
