@@ -10,6 +10,7 @@
 //   - split-bf16 operands, 3 MMAs per K-step (hi*hi + lo*hi + hi*lo), fp32 accumulation in TMEM.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -48,6 +49,89 @@ struct GemmKernelArgs {
   int y_ld;
   int passes;
 };
+
+// bias / activation / residual / row mask / stores for one 32-column chunk of one output row (v: the accumulators)
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmKernelArgs& p, float (&v)[32], const int nb, const bool row_ok,
+                                                    const bool row_live, const long long y_off) {
+  if (row_ok && nb < p.n) {
+    // bias: one batch of independent loads per 32-column chunk (a dependent load per element would serialise the
+    // epilogue on global-memory latency), activation selected outside the element loops
+    float bv[32];
+    if (p.bias == nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+    } else if (nb + 32 <= p.n && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        bv[4 * j] = b.x; bv[4 * j + 1] = b.y; bv[4 * j + 2] = b.z; bv[4 * j + 3] = b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bv[j] = nb + j < p.n ? __ldg(p.bias + nb + j) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.scale, bv[j]);
+    if (p.act == PK_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (p.act == PK_ACT_TANH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    }
+    const bool full = (nb + 32 <= p.n) && ((p.y_ld & 7) == 0) && (((y_off + nb) & 7) == 0);
+    if (p.residual != nullptr) {
+      if (full) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + y_off + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = __ldg(r4 + j);
+          v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.n) v[j] += __ldg(p.residual + y_off + nb + j);
+      }
+    }
+    if (!row_live) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    if (full) {
+      if (p.y_f32 != nullptr) {
+        float4* o4 = reinterpret_cast<float4*>(p.y_f32 + y_off + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (p.y_hi != nullptr) {
+        uint4* oh = reinterpret_cast<uint4*>(p.y_hi + y_off + nb);
+        uint4* ol = reinterpret_cast<uint4*>(p.y_lo + y_off + nb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 h, l;
+          split8(v + 8 * j, h, l);
+          oh[j] = h;
+          ol[j] = l;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (nb + j < p.n) {
+          if (p.y_f32 != nullptr) p.y_f32[y_off + nb + j] = v[j];
+          if (p.y_hi != nullptr) {
+            __nv_bfloat16 h, l;
+            split_bf16(v[j], h, l);
+            p.y_hi[y_off + nb + j] = h;
+            p.y_lo[y_off + nb + j] = l;
+          }
+        }
+      }
+    }
+  }
+}
 
 struct GemmTile {     // persistent tile schedule: m-tile fastest, then (batch, head), then n-tile, so that the CTAs
   int m0, n0, bz, hz; // running at the same time share one n-tile of B (the weights stay hot in L2)
@@ -193,85 +277,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           tcgen05_fence_before();
           mbar_arrive(&acc_empty[buf]);
         }
-        const int nb = t.n0 + c * 32;
-        if (row_ok && nb < p.n) {
-          // bias: one batch of independent loads per 32-column chunk (a dependent load per element would serialise the
-          // epilogue on global-memory latency), activation selected outside the element loops
-          float bv[32];
-          if (p.bias == nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = 0.f;
-          } else if (nb + 32 <= p.n && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              bv[4 * j] = b.x; bv[4 * j + 1] = b.y; bv[4 * j + 2] = b.z; bv[4 * j + 3] = b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = nb + j < p.n ? __ldg(p.bias + nb + j) : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], p.scale, bv[j]);
-          if (p.act == PK_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == PK_ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          }
-          const bool full = (nb + 32 <= p.n) && ((p.y_ld & 7) == 0) && (((y_off + nb) & 7) == 0);
-          if (p.residual != nullptr) {
-            if (full) {
-              const float4* r4 = reinterpret_cast<const float4*>(p.residual + y_off + nb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = __ldg(r4 + j);
-                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.n) v[j] += __ldg(p.residual + y_off + nb + j);
-            }
-          }
-          if (!row_live) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          if (full) {
-            if (p.y_f32 != nullptr) {
-              float4* o4 = reinterpret_cast<float4*>(p.y_f32 + y_off + nb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.y_hi != nullptr) {
-              uint4* oh = reinterpret_cast<uint4*>(p.y_hi + y_off + nb);
-              uint4* ol = reinterpret_cast<uint4*>(p.y_lo + y_off + nb);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 h, l;
-                split8(v + 8 * j, h, l);
-                oh[j] = h;
-                ol[j] = l;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (nb + j < p.n) {
-                if (p.y_f32 != nullptr) p.y_f32[y_off + nb + j] = v[j];
-                if (p.y_hi != nullptr) {
-                  __nv_bfloat16 h, l;
-                  split_bf16(v[j], h, l);
-                  p.y_hi[y_off + nb + j] = h;
-                  p.y_lo[y_off + nb + j] = l;
-                }
-              }
-            }
-          }
-        }
+        gemm_epilogue_chunk(p, v, t.n0 + c * 32, row_ok, row_live, y_off);
       }
     }
     tcgen05_fence_before();
@@ -280,6 +286,182 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<2 * Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2, clusters of 2) for wide outputs: one M = 256 x BLOCK_N tile per pair.
+// Each CTA loads its own 128 rows of A and HALF of the B tile (BLOCK_N / 2 rows), so the L2 -> SM operand stream per CTA
+// drops from 96 KB to 64 KB per K-chunk at BLOCK_N = 256 (the single-CTA kernel needs 62 B/clk/SM there against a
+// 42 B/clk/SM share of the L2 throughput cap) and three 64 KB stages fit instead of two 96 KB ones.
+// Leader CTA (cluster rank 0): issues every MMA / commit, owns full[s] (TMA bytes of both CTAs) and acc_empty[2]
+// (warp-elected relaxed remote arrivals); both CTAs: producer, epilogue, local empty[s] / acc_full[2] (multicast commits).
+// ---------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct GemmPairCfg {
+  static constexpr int kABytes = kBlockM * kSwizzleBytes;             // one plane of this CTA's A chunk (16 KB)
+  static constexpr int kBBytes = (BLOCK_N / 2) * kSwizzleBytes;       // one plane of this CTA's half of the B chunk
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = 3;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr uint32_t kTmemCols = BLOCK_N;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                      const GemmKernelArgs p) {
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t full_bar = bars;                              // [stages] (the leader's copy is live)
+  const uint32_t empty_bar = full_bar + 8 * Cfg::kStages;      // [stages]
+  const uint32_t acc_full = empty_bar + 8 * Cfg::kStages;      // [2]
+  const uint32_t acc_empty = acc_full + 16;                    // [2] leader
+  const uint32_t tmem_slot = acc_empty + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_chunks = p.taps * p.k_chunks;
+  const int zdim = p.batch * p.heads;
+  const int pair_id = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init_a(full_bar + 8 * s, 1);
+      mbar_init_a(empty_bar + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init_a(acc_full + 8 * i, 1);
+      mbar_init_a(acc_empty + 8 * i, 2 * 4);                   // 4 epilogue warps in each CTA, one elected arrival each
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm_a<2 * Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = lds_u32(tmem_slot);
+
+  // tile schedule of the pair: m-pair-tile (256 rows) fastest, then (batch, head), then n-tile; p.tiles_m counts pair tiles
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer (both CTAs) ------------------------------
+      const uint32_t full_leader = mapa_shared(full_bar, 0);
+      const uint32_t tx_bytes = 2 * ((p.passes == 3) ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes));   // both CTAs
+      uint32_t it = 0;
+      for (int tile = pair_id; tile < p.total_tiles; tile += pair_step) {
+        const int mt = tile % p.tiles_m;
+        const int r = tile / p.tiles_m;
+        const int z = r % zdim;
+        const int m0 = mt * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
+        const int n0 = (r / zdim) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        const int bz = z / p.heads, hz = z % p.heads;
+        const int a_batch = bz * p.a_bmul + hz * p.a_hmul;
+        const int b_batch = bz * p.b_bmul + hz * p.b_hmul;
+        const int a_col = p.a_col0 + hz * p.a_colh;
+        const int b_col = p.b_col0 + hz * p.b_colh;
+        for (int i = 0; i < num_chunks; ++i, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          const int tap = i / p.k_chunks;
+          const int kc = i % p.k_chunks;
+          mbar_wait_a(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t st = smem + s * Cfg::kStageBytes;
+          const uint32_t fb = full_leader + 8 * s;
+          if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, tx_bytes);
+          const int a_row = m0 + (tap - p.pad) * p.dil;
+          const int bc = b_col + tap * p.b_tap_stride + kc * kChunkK;
+          tma_load_3d_2sm_a(st, &tm_a_hi, fb, a_col + kc * kChunkK, a_row, a_batch);
+          tma_load_3d_2sm_a(st + 2 * Cfg::kABytes, &tm_b_hi, fb, bc, n0, b_batch);
+          if (p.passes == 3) {
+            tma_load_3d_2sm_a(st + Cfg::kABytes, &tm_a_lo, fb, a_col + kc * kChunkK, a_row, a_batch);
+            tma_load_3d_2sm_a(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, fb, bc, n0, b_batch);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------ MMA issuer (leader CTA) ------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = pair_id; tile < p.total_tiles; tile += pair_step, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait_a(acc_empty + 8 * buf, ((lt >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * Cfg::kTmemCols;
+        for (int i = 0; i < num_chunks; ++i, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait_a(full_bar + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t st = smem + s * Cfg::kStageBytes;
+          const uint64_t a_hi = make_smem_desc_sw128(st);
+          const uint64_t a_lo = make_smem_desc_sw128(st + Cfg::kABytes);
+          const uint64_t b_hi = make_smem_desc_sw128(st + 2 * Cfg::kABytes);
+          const uint64_t b_lo = make_smem_desc_sw128(st + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, (i | k) != 0);
+            if (p.passes == 3) {
+              umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+              umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+            }
+          }
+          umma_commit_2sm_a(empty_bar + 8 * s);
+        }
+        umma_commit_2sm_a(acc_full + 8 * buf);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 rows, all BLOCK_N columns) ------------------------------
+    const int quarter = warp & 3;
+    const uint32_t acc_empty_l = mapa_shared(acc_empty, 0);
+    int lt = 0;
+    for (int tile = pair_id; tile < p.total_tiles; tile += pair_step, ++lt) {
+      const int mt = tile % p.tiles_m;
+      const int r = tile / p.tiles_m;
+      const int z = r % zdim;
+      const int tn0 = (r / zdim) * BLOCK_N;
+      const int bz = z / p.heads, hz = z % p.heads;
+      const int buf = lt & 1;
+      const int row = mt * 2 * kBlockM + static_cast<int>(rank) * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < p.m;
+      const bool row_live = row_ok && (p.lens == nullptr || row < __ldg(p.lens + bz));
+      const long long y_off = bz * p.y_batch_stride + hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
+      mbar_wait_a(acc_full + 8 * buf, (lt >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kTmemCols + c * 32, v);
+        tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed_a(acc_empty_l + 8 * buf);
+        }
+        gemm_epilogue_chunk(p, v, tn0 + c * 32, row_ok, row_live, y_off);
+      }
+    }
+    tcgen05_fence_before();
+  }
+  cluster_sync();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<2 * Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -395,6 +577,37 @@ static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
   return PK_OK;
 }
 
+template <int BLOCK_N>
+static int launch_pair(const pk_conv_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmPairCfg<BLOCK_N>;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = encode_tmap_bf16_3d(&ta_hi, a->a.hi, a->a.cols, a->a.rows, a->a.batches, a->a.ld, a->a.batch_stride, kBlockM))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tb_hi, a->b.hi, a->b.cols, a->b.rows, a->b.batches, a->b.ld, a->b.batch_stride, BLOCK_N / 2))) return rc;
+  if (a->passes == 3) {
+    if ((rc = encode_tmap_bf16_3d(&ta_lo, a->a.lo, a->a.cols, a->a.rows, a->a.batches, a->a.ld, a->a.batch_stride, kBlockM))) return rc;
+    if ((rc = encode_tmap_bf16_3d(&tb_lo, a->b.lo, a->b.cols, a->b.rows, a->b.batches, a->b.ld, a->b.batch_stride, BLOCK_N / 2))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  GemmKernelArgs p = to_kernel_args(a);
+  p.tiles_m = (a->m + 2 * kBlockM - 1) / (2 * kBlockM);        // pair tiles of 256 rows
+  const long long total = static_cast<long long>(p.tiles_m) * ((a->n + BLOCK_N - 1) / BLOCK_N) * a->batch * a->heads;
+  PK_CHECK_ARG(total < (1LL << 31), "too many output tiles");
+  p.total_tiles = static_cast<int>(total);
+  const int grid = 2 * static_cast<int>(std::min<long long>(total, sm_count() / 2));
+  conv_gemm_pair_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
 }  // namespace pk
 
 extern "C" int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream) {
@@ -405,7 +618,15 @@ extern "C" int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream) {
   const int n = args->n;
   auto waste = [n](int bn) { return (n + bn - 1) / bn * bn - n; };
   if (n <= 64) return pk::launch<64>(args, s);
-  if (waste(256) <= waste(128) && n > 128) return pk::launch<256>(args, s);
+  if (waste(256) <= waste(128) && n > 128) {
+    // wide outputs: CTA pairs (half of the B tile per CTA) unless PK_GEMM_PAIR=0 or the rows fit one 128-row tile
+    static const bool use_pair = []() {
+      const char* e = getenv("PK_GEMM_PAIR");
+      return !(e && e[0] == '0') && pk::sm_count() >= 2;
+    }();
+    if (use_pair && args->m > 128) return pk::launch_pair<256>(args, s);
+    return pk::launch<256>(args, s);
+  }
   return pk::launch<128>(args, s);
 }
 
