@@ -304,7 +304,7 @@ struct GemmPairCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = 3;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr uint32_t kTmemCols = BLOCK_N;
+  static constexpr uint32_t kTmemCols = BLOCK_N <= 128 ? 128 : 256;   // accumulator stride (2 buffers: power-of-two allocation)
 };
 
 template <int BLOCK_N>
@@ -577,6 +577,14 @@ static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
   return PK_OK;
 }
 
+static bool use_pair() {
+  static const bool v = []() {
+    const char* e = getenv("PK_GEMM_PAIR");
+    return !(e && e[0] == '0') && sm_count() >= 2;
+  }();
+  return v;
+}
+
 template <int BLOCK_N>
 static int launch_pair(const pk_conv_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmPairCfg<BLOCK_N>;
@@ -620,13 +628,12 @@ extern "C" int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream) {
   if (n <= 64) return pk::launch<64>(args, s);
   if (waste(256) <= waste(128) && n > 128) {
     // wide outputs: CTA pairs (half of the B tile per CTA) unless PK_GEMM_PAIR=0 or the rows fit one 128-row tile
-    static const bool use_pair = []() {
-      const char* e = getenv("PK_GEMM_PAIR");
-      return !(e && e[0] == '0') && pk::sm_count() >= 2;
-    }();
-    if (use_pair && args->m > 128) return pk::launch_pair<256>(args, s);
+    if (pk::use_pair() && args->m > 128) return pk::launch_pair<256>(args, s);
     return pk::launch<256>(args, s);
   }
+  // N = 384 / 1152 / ... : 192-wide pair tiles have no padded columns and a pair instruction of 96 clk of work
+  if (pk::use_pair() && args->m > 128 && n >= 384 && waste(192) < waste(256) && waste(192) <= waste(128))
+    return pk::launch_pair<192>(args, s);
   return pk::launch<128>(args, s);
 }
 
