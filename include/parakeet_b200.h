@@ -94,6 +94,31 @@ typedef struct pk_conv_gemm_args {
 
 int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream);
 
+/* pk_conv_gemm with a fused pair epilogue: the output row has n = 2 * channels columns, column c of the first half is
+ * combined with column channels + c of the second half (bias and scale applied to both) and the GEMM result itself is
+ * never written.  n <= 256, channels % 32 == 0, heads == 1; act / residual / lens of the base arguments must be unset.
+ *   PK_EPI_GATE       z = tanh(a + res_a) * sigmoid(g + res_g) written as split planes y_hi / y_lo (batch, m, y_ld);
+ *                     `residual` (fp32, batch stride / row pitch given, 2 * channels columns) may be NULL.  Fuses the gate of
+ *                     waveflow.ResidualBlock (models/waveflow.py:277-281) into its dilated-conv GEMM.
+ *   PK_EPI_WF_UPDATE  state (batch, m, channels) += a;  skip = skip_init ? g : skip + g;  the new state is also written as
+ *                     split planes into buf_hi / buf_lo (batch, m, buf_ld) at column buf_col0 when given.  Fuses
+ *                     `res, skip = split(out_proj(z))` (models/waveflow.py:282-294) and ResidualNet.add_input (:386-392). */
+enum { PK_EPI_NONE = 0, PK_EPI_GATE = 1, PK_EPI_WF_UPDATE = 2 };
+typedef struct pk_gemm_epilogue {
+  int32_t mode;                  /* PK_EPI_* */
+  int32_t channels;              /* C: n == 2 * C */
+  const float* residual;         /* GATE */
+  int64_t residual_batch_stride;
+  int32_t residual_ld;
+  int32_t skip_init;             /* WF_UPDATE */
+  float* state;
+  float* skip;
+  void* buf_hi;
+  void* buf_lo;
+  int32_t buf_ld, buf_col0;
+} pk_gemm_epilogue;
+int pk_conv_gemm_ex(const pk_conv_gemm_args* args, const pk_gemm_epilogue* epilogue, pk_stream_t stream);
+
 /* Same contract evaluated with plain fp32 FMAs (one thread per output element).  Debug / cross-check kernel for
  * the tensor-core path at sizes where the CPU oracle is too slow; not used by the models. */
 int pk_conv_gemm_simt(const pk_conv_gemm_args* args, pk_stream_t stream);

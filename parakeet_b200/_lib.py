@@ -30,6 +30,14 @@ class ConvGemmArgs(C.Structure):
                 ("passes", C.c_int32)]
 
 
+class GemmEpilogue(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("channels", C.c_int32), ("residual", C.c_void_p), ("residual_batch_stride", C.c_int64),
+                ("residual_ld", C.c_int32), ("skip_init", C.c_int32), ("state", C.c_void_p), ("skip", C.c_void_p),
+                ("buf_hi", C.c_void_p), ("buf_lo", C.c_void_p), ("buf_ld", C.c_int32), ("buf_col0", C.c_int32)]
+
+
+PK_EPI_NONE, PK_EPI_GATE, PK_EPI_WF_UPDATE = 0, 1, 2
+
 _lib = None
 
 
@@ -63,6 +71,7 @@ def _declare(L):
         "pk_split_f32": [vp, vp, vp, i64, vp],
         "pk_conv_gemm": [C.POINTER(ConvGemmArgs), vp],
         "pk_conv_gemm_simt": [C.POINTER(ConvGemmArgs), vp],
+        "pk_conv_gemm_ex": [C.POINTER(ConvGemmArgs), C.POINTER(GemmEpilogue), vp],
         "pk_length_regulator_lens": [vp, i32, i32, vp, vp],
         "pk_length_regulate": [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
         "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],

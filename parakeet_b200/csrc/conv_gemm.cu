@@ -48,6 +48,17 @@ struct GemmKernelArgs {
   long long y_batch_stride, y_head_stride;
   int y_ld;
   int passes;
+  // fused pair epilogues (pk_conv_gemm_ex): the tile covers n = 2 * epi_c columns, column c is paired with column epi_c + c
+  int epi, epi_c;
+  const float* e_res;            // GATE: fp32 (batch, m, e_res_ld) added before the gate, or NULL
+  long long e_res_bs;
+  int e_res_ld;
+  float* e_state;                // WF_UPDATE: fp32 (batch, m, epi_c) running state / skip sum
+  float* e_skip;
+  int e_skip_init;
+  __nv_bfloat16* e_buf_hi;       // WF_UPDATE: optional split planes (batch, m, e_buf_ld) receiving the new state at e_buf_col0
+  __nv_bfloat16* e_buf_lo;
+  int e_buf_ld, e_buf_col0;
 };
 
 // bias / activation / residual / row mask / stores for one 32-column chunk of one output row (v: the accumulators)
@@ -128,6 +139,80 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmKernelArgs& p, flo
             p.y_lo[y_off + nb + j] = l;
           }
         }
+      }
+    }
+  }
+}
+
+// Fused pair epilogues: one 32-column chunk of the first half (va: columns [nb, nb+32) of [0, C)) together with the
+// matching chunk of the second half (vg: columns C + [nb, nb+32)); bias / scale applied to both.
+//   PK_EPI_GATE      z = tanh(a + res_a) * sigmoid(g + res_g) -> split planes (batch, m, y_ld) at column nb
+//                    (ResidualBlock gate of waveflow.py:277-281 fused into the dilated-conv GEMM)
+//   PK_EPI_WF_UPDATE state += a; skip (=|+=) g; new state -> optional split planes
+//                    (waveflow.py:282-294 `res, skip = split(out_proj(z))`, ResidualNet.add_input :386-392)
+__device__ __forceinline__ void gemm_epilogue_pair(const GemmKernelArgs& p, float (&va)[32], float (&vg)[32], const int nb,
+                                                   const int bz, const int row, const bool row_ok) {
+  if (!row_ok) return;
+  const int C = p.epi_c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+    if (p.bias != nullptr) {
+      ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+      bg = __ldg(reinterpret_cast<const float4*>(p.bias + C + nb) + j);
+    }
+    va[4 * j] = fmaf(va[4 * j], p.scale, ba.x); va[4 * j + 1] = fmaf(va[4 * j + 1], p.scale, ba.y);
+    va[4 * j + 2] = fmaf(va[4 * j + 2], p.scale, ba.z); va[4 * j + 3] = fmaf(va[4 * j + 3], p.scale, ba.w);
+    vg[4 * j] = fmaf(vg[4 * j], p.scale, bg.x); vg[4 * j + 1] = fmaf(vg[4 * j + 1], p.scale, bg.y);
+    vg[4 * j + 2] = fmaf(vg[4 * j + 2], p.scale, bg.z); vg[4 * j + 3] = fmaf(vg[4 * j + 3], p.scale, bg.w);
+  }
+  const long long grow = static_cast<long long>(bz) * p.m + row;       // row index in (batch, m, .) tensors
+  if (p.epi == PK_EPI_GATE) {
+    if (p.e_res != nullptr) {
+      const float4* ra = reinterpret_cast<const float4*>(p.e_res + bz * p.e_res_bs + static_cast<long long>(row) * p.e_res_ld + nb);
+      const float4* rg = reinterpret_cast<const float4*>(p.e_res + bz * p.e_res_bs + static_cast<long long>(row) * p.e_res_ld + C + nb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = __ldg(ra + j), y = __ldg(rg + j);
+        va[4 * j] += x.x; va[4 * j + 1] += x.y; va[4 * j + 2] += x.z; va[4 * j + 3] += x.w;
+        vg[4 * j] += y.x; vg[4 * j + 1] += y.y; vg[4 * j + 2] += y.z; vg[4 * j + 3] += y.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) va[j] = tanhf(va[j]) * (1.f / (1.f + expf(-vg[j])));
+    uint4* oh = reinterpret_cast<uint4*>(p.y_hi + grow * p.y_ld + nb);
+    uint4* ol = reinterpret_cast<uint4*>(p.y_lo + grow * p.y_ld + nb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 h, l;
+      split8(va + 8 * j, h, l);
+      oh[j] = h;
+      ol[j] = l;
+    }
+  } else {   // PK_EPI_WF_UPDATE
+    float4* st4 = reinterpret_cast<float4*>(p.e_state + grow * C + nb);
+    float4* sk4 = reinterpret_cast<float4*>(p.e_skip + grow * C + nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s = st4[j];
+      va[4 * j] += s.x; va[4 * j + 1] += s.y; va[4 * j + 2] += s.z; va[4 * j + 3] += s.w;
+      st4[j] = make_float4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]);
+      float4 k = make_float4(vg[4 * j], vg[4 * j + 1], vg[4 * j + 2], vg[4 * j + 3]);
+      if (!p.e_skip_init) {
+        const float4 o = sk4[j];
+        k.x += o.x; k.y += o.y; k.z += o.z; k.w += o.w;
+      }
+      sk4[j] = k;
+    }
+    if (p.e_buf_hi != nullptr) {
+      uint4* oh = reinterpret_cast<uint4*>(p.e_buf_hi + grow * p.e_buf_ld + p.e_buf_col0 + nb);
+      uint4* ol = reinterpret_cast<uint4*>(p.e_buf_lo + grow * p.e_buf_ld + p.e_buf_col0 + nb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 h, l;
+        split8(va + 8 * j, h, l);
+        oh[j] = h;
+        ol[j] = l;
       }
     }
   }
@@ -267,17 +352,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const long long y_off = t.bz * p.y_batch_stride + t.hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kTmemCols;
+      if (p.epi == PK_EPI_NONE) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        float v[32];
-        __syncwarp();
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kTmemCols + c * 32, v);
-        tmem_ld_wait();
-        if (c == BLOCK_N / 32 - 1) {            // last read of this accumulator: hand it back to the MMA issuer
-          tcgen05_fence_before();
-          mbar_arrive(&acc_empty[buf]);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(t_acc + c * 32, v);
+          tmem_ld_wait();
+          if (c == BLOCK_N / 32 - 1) {            // last read of this accumulator: hand it back to the MMA issuer
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+          }
+          gemm_epilogue_chunk(p, v, t.n0 + c * 32, row_ok, row_live, y_off);
         }
-        gemm_epilogue_chunk(p, v, t.n0 + c * 32, row_ok, row_live, y_off);
+      } else {
+        // fused pair epilogues: the tile holds columns [0, 2C); chunk c of the first half with chunk c of the second half
+        const int hc = p.epi_c / 32;
+#pragma unroll 1
+        for (int c = 0; c < hc; ++c) {
+          float va[32], vg[32];
+          __syncwarp();
+          tmem_ld_32x32(t_acc + c * 32, va);
+          tmem_ld_32x32(t_acc + p.epi_c + c * 32, vg);
+          tmem_ld_wait();
+          if (c == hc - 1) {
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+          }
+          gemm_epilogue_pair(p, va, vg, c * 32, t.bz, row, row_ok);
+        }
       }
     }
     tcgen05_fence_before();
@@ -515,7 +619,7 @@ __global__ void conv_gemm_simt_kernel(const __nv_bfloat16* a_hi, const __nv_bflo
   }
 }
 
-static int validate(const pk_conv_gemm_args* a) {
+static int validate_common(const pk_conv_gemm_args* a) {
   PK_CHECK_ARG(a != nullptr, "args is NULL");
   PK_CHECK_ARG(a->a.hi && a->b.hi, "operand hi planes must be non-NULL");
   PK_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3 (got %d)", a->passes);
@@ -526,9 +630,37 @@ static int validate(const pk_conv_gemm_args* a) {
   PK_CHECK_ARG((a->a.batch_stride % 8) == 0 && (a->b.batch_stride % 8) == 0, "operand batch strides must be multiples of 8");
   PK_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a.hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b.hi) & 15) == 0,
                "operand planes must be 16-byte aligned");
-  PK_CHECK_ARG((a->y_f32 != nullptr) || (a->y_hi != nullptr), "no output requested");
   PK_CHECK_ARG((a->y_hi == nullptr) == (a->y_lo == nullptr), "y_hi and y_lo must both be set or both NULL");
   PK_CHECK_ARG(a->act >= PK_ACT_NONE && a->act <= PK_ACT_TANH, "unknown activation %d", a->act);
+  return PK_OK;
+}
+
+static int validate(const pk_conv_gemm_args* a) {
+  int rc = validate_common(a);
+  if (rc) return rc;
+  PK_CHECK_ARG((a->y_f32 != nullptr) || (a->y_hi != nullptr), "no output requested");
+  return PK_OK;
+}
+
+static int validate_epilogue(const pk_conv_gemm_args* a, const pk_gemm_epilogue* e) {
+  int rc = validate_common(a);
+  if (rc) return rc;
+  PK_CHECK_ARG(e->mode == PK_EPI_GATE || e->mode == PK_EPI_WF_UPDATE, "unknown epilogue mode %d", e->mode);
+  PK_CHECK_ARG(e->channels > 0 && (e->channels % 32) == 0 && a->n == 2 * e->channels && a->n <= 256,
+               "fused epilogues need n == 2 * channels, channels %% 32 == 0, n <= 256 (n=%d channels=%d)", a->n, e->channels);
+  PK_CHECK_ARG(a->heads == 1 && a->act == PK_ACT_NONE && a->residual == nullptr && a->lens == nullptr,
+               "fused epilogues take heads == 1, no activation / residual / lens in the base arguments");
+  PK_CHECK_ARG(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "bias must be 16-byte aligned");
+  if (e->mode == PK_EPI_GATE) {
+    PK_CHECK_ARG(a->y_hi && a->y_lo && (a->y_ld % 8) == 0, "GATE writes split planes (y_hi / y_lo), y_ld %% 8 == 0");
+    PK_CHECK_ARG(e->residual == nullptr || ((e->residual_ld % 4) == 0 && (e->residual_batch_stride % 4) == 0 &&
+                                            (reinterpret_cast<uintptr_t>(e->residual) & 15) == 0),
+                 "GATE residual must be 16-byte aligned with strides %% 4 == 0");
+  } else {
+    PK_CHECK_ARG(e->state && e->skip, "WF_UPDATE needs state and skip");
+    PK_CHECK_ARG((e->buf_hi == nullptr) == (e->buf_lo == nullptr), "buf_hi and buf_lo must both be set or both NULL");
+    PK_CHECK_ARG(e->buf_hi == nullptr || ((e->buf_ld % 8) == 0 && (e->buf_col0 % 8) == 0), "buf_ld / buf_col0 must be multiples of 8");
+  }
   return PK_OK;
 }
 
@@ -543,11 +675,13 @@ static GemmKernelArgs to_kernel_args(const pk_conv_gemm_args* a) {
   p.y_f32 = a->y_f32; p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
   p.y_batch_stride = a->y_batch_stride; p.y_head_stride = a->y_head_stride; p.y_ld = a->y_ld;
   p.passes = a->passes;
+  p.epi = PK_EPI_NONE; p.epi_c = 0; p.e_res = nullptr; p.e_res_bs = 0; p.e_res_ld = 0; p.e_state = nullptr; p.e_skip = nullptr;
+  p.e_skip_init = 0; p.e_buf_hi = nullptr; p.e_buf_lo = nullptr; p.e_buf_ld = 0; p.e_buf_col0 = 0;
   return p;
 }
 
 template <int BLOCK_N>
-static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
+static int launch(const pk_conv_gemm_args* a, cudaStream_t stream, const pk_gemm_epilogue* e = nullptr) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
@@ -566,6 +700,12 @@ static int launch(const pk_conv_gemm_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   GemmKernelArgs p = to_kernel_args(a);
+  if (e != nullptr) {
+    p.epi = e->mode; p.epi_c = e->channels; p.e_res = e->residual; p.e_res_bs = e->residual_batch_stride; p.e_res_ld = e->residual_ld;
+    p.e_state = e->state; p.e_skip = e->skip; p.e_skip_init = e->skip_init;
+    p.e_buf_hi = static_cast<__nv_bfloat16*>(e->buf_hi); p.e_buf_lo = static_cast<__nv_bfloat16*>(e->buf_lo);
+    p.e_buf_ld = e->buf_ld; p.e_buf_col0 = e->buf_col0;
+  }
   p.tiles_m = (a->m + kBlockM - 1) / kBlockM;
   const long long total = static_cast<long long>(p.tiles_m) * ((a->n + BLOCK_N - 1) / BLOCK_N) * a->batch * a->heads;
   PK_CHECK_ARG(total < (1LL << 31), "too many output tiles");
@@ -635,6 +775,15 @@ extern "C" int pk_conv_gemm(const pk_conv_gemm_args* args, pk_stream_t stream) {
   if (pk::use_pair() && args->m > 128 && n >= 384 && waste(192) < waste(256) && waste(192) <= waste(128))
     return pk::launch_pair<192>(args, s);
   return pk::launch<128>(args, s);
+}
+
+extern "C" int pk_conv_gemm_ex(const pk_conv_gemm_args* args, const pk_gemm_epilogue* epi, pk_stream_t stream) {
+  if (epi == nullptr || epi->mode == PK_EPI_NONE) return pk_conv_gemm(args, stream);
+  int rc = pk::validate_epilogue(args, epi);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the whole 2C-wide row must sit in one tile of the single-CTA kernel
+  return args->n <= 128 ? pk::launch<128>(args, s, epi) : pk::launch<256>(args, s, epi);
 }
 
 extern "C" int pk_conv_gemm_simt(const pk_conv_gemm_args* args, pk_stream_t stream) {

@@ -103,8 +103,12 @@ class ConditionalWaveFlow(Layer):
                                    cond=ops.pack_weight(p[q + "condition_proj.weight"][:, :, 0, 0], dev),
                                    cond_b=p[q + "condition_proj.bias"].to(dev),
                                    out=ops.pack_weight(p[q + "out_proj.weight"][:, :, 0, 0], dev), out_b=p[q + "out_proj.bias"].to(dev)))
+            # the condition projections of all layers of a flow in one GEMM per row step (they do not depend on the recurrence)
+            cond_w = torch.cat([p[f"{pre}resnet.{l}.condition_proj.weight"][:, :, 0, 0] for l in range(self.n_layers)], dim=0)
+            cond_b = torch.cat([p[f"{pre}resnet.{l}.condition_proj.bias"] for l in range(self.n_layers)])
             pk["flows"].append(dict(in_w=p[pre + "input_proj.weight"].reshape(-1).contiguous().to(dev),
                                     in_b=p[pre + "input_proj.bias"].to(dev), layers=layers,
+                                    cond_all=ops.pack_weight(cond_w, dev), cond_all_b=cond_b.contiguous().to(dev),
                                     out_w=p[pre + "output_proj.weight"].reshape(2, C).contiguous().to(dev),
                                     out_b=p[pre + "output_proj.bias"].to(dev)))
         pk["perms"] = [torch.tensor(pm, dtype=torch.int64, device=dev) for pm in self.perms]   # device-side gather indices
@@ -140,12 +144,10 @@ class ConditionalWaveFlow(Layer):
         cmap = list(range(G))                                                             # cumulative row permutation of the condition
         state = torch.empty(B, W, C, device=dev)
         skip = torch.empty(B, W, C, device=dev)
-        h = torch.empty(B, W, 2 * C, device=dev)
-        o = torch.empty(B, W, 2 * C, device=dev)
+        h_all = torch.empty(B, W, NL * 2 * C, device=dev)                                 # condition projections of one row step
         zt = Split.empty((B, W, C), dev)
         bufs = [Split.zeros((B, W, 3 * C), dev) for _ in range(NL)]
         st = _stream()
-        rows = B * W
         for fi in reversed(range(self.n_flows)):
             perm = self.perms[fi]
             z = z.index_select(1, pk["perms"][fi])                                        # geo.shuffle_dim(z, 2, perm)
@@ -162,15 +164,16 @@ class ConditionalWaveFlow(Layer):
                                                     _ptr(state), _ptr(bufs[0].hi), _ptr(bufs[0].lo), 3 * C, slot * C, st),
                            "pk_waveflow_input_proj")
                 c_row = Split(cond_s.hi[:, cmap[i]], cond_s.lo[:, cmap[i]])              # (B, W, n_mels) views, batch stride G*W*n_mels
+                ops.conv_gemm(c_row, fw["cond_all"], n=NL * 2 * C, k=self.n_mels, bias=fw["cond_all_b"], y_f32=h_all)
                 for l, lay in enumerate(fw["layers"]):
-                    ops.conv_gemm(bufs[l], lay["conv"][i % 3], n=2 * C, k=3 * C, taps=3, dil=2 ** l, bias=lay["conv_b"], y_f32=h)
-                    ops.conv_gemm(c_row, lay["cond"], n=2 * C, k=self.n_mels, bias=lay["cond_b"], residual=h, y_f32=h)
-                    _lib.check(L.pk_gated_activation(_ptr(h), rows, C, _ptr(zt.hi), _ptr(zt.lo), st), "pk_gated_activation")
-                    ops.conv_gemm(zt, lay["out"], n=2 * C, k=C, bias=lay["out_b"], y_f32=o)
+                    # dilated conv over the 3-row ring + condition slice -> tanh * sigmoid, fused in the GEMM epilogue
+                    ops.conv_gemm(bufs[l], lay["conv"][i % 3], n=2 * C, k=3 * C, taps=3, dil=2 ** l, bias=lay["conv_b"], y_split=zt,
+                                  epilogue=dict(mode="gate", channels=C, residual=h_all[:, :, l * 2 * C:(l + 1) * 2 * C]))
+                    # out_proj -> (res | skip): state += res, skip += skip, next layer's ring slot <- new state, in the epilogue
                     nxt = bufs[l + 1] if l + 1 < NL else None
-                    _lib.check(L.pk_waveflow_layer_update(_ptr(o), rows, C, _ptr(state), _ptr(skip), 1 if l == 0 else 0,
-                                                          _ptr(nxt.hi) if nxt else None, _ptr(nxt.lo) if nxt else None, 3 * C,
-                                                          slot * C, st), "pk_waveflow_layer_update")
+                    ops.conv_gemm(zt, lay["out"], n=2 * C, k=C, bias=lay["out_b"],
+                                  epilogue=dict(mode="wf_update", channels=C, state=state, skip=skip, skip_init=(l == 0), buf=nxt,
+                                                buf_col0=slot * C))
                 _lib.check(L.pk_waveflow_row_out(_ptr(skip), _ptr(fw["out_w"]), _ptr(fw["out_b"]), _ptr(z[:, i]), G * W, B, W, C,
                                                  _ptr(x[:, i]), G * W, st), "pk_waveflow_row_out")
             z = x

@@ -84,16 +84,25 @@ def _operand(s, rows, cols, ld, batch_stride, batches, bmul=1, hmul=0, col0=0, c
 
 
 def conv_gemm(a, w, *, n, k, taps=1, dil=1, pad=None, bias=None, act=None, residual=None, lens=None, scale=1.0,
-              out_f32=True, out_split=False, passes=3, simt=False, y_f32=None, y_split=None):
+              out_f32=True, out_split=False, passes=3, simt=False, y_f32=None, y_split=None, epilogue=None):
     """Channels-last Conv1D / Linear.  a: Split (B, T, C_total); w: packed weight Split [n, taps*Kp].
 
     Returns (y_f32 or None, y_split or None), each (B, T, n).
+    `epilogue` selects a fused pair epilogue of pk_conv_gemm_ex (n == 2 * C, the GEMM result itself is not written):
+      dict(mode="gate", channels=C, residual=(tensor (B, T, >= 2C) fp32 view with last stride 1) or None) -> y_split (B, T, C)
+      dict(mode="wf_update", channels=C, state=, skip=, skip_init=bool, buf=Split or None, buf_col0=int)
     """
     _require_cuda(a.hi, w.hi)
     B, T, Ctot = a.hi.shape
     if pad is None:
         pad = (taps - 1) // 2
     dev = a.hi.device
+    if epilogue is not None:
+        out_f32 = False
+        out_split = False
+        y_f32 = None
+        if epilogue["mode"] == "gate" and y_split is None:
+            y_split = Split.empty((B, T, epilogue["channels"]), dev)
     if out_f32 and y_f32 is None:
         y_f32 = torch.empty(B, T, n, dtype=torch.float32, device=dev)
     if out_split and y_split is None:
@@ -113,6 +122,28 @@ def conv_gemm(a, w, *, n, k, taps=1, dil=1, pad=None, bias=None, act=None, resid
     args.y_lo = y_split.lo.data_ptr() if y_split is not None else None
     args.y_batch_stride, args.y_head_stride, args.y_ld = T * n, 0, n
     args.passes = passes
+    if epilogue is not None:
+        ep = _lib.GemmEpilogue()
+        Cc = int(epilogue["channels"])
+        ep.channels = Cc
+        if epilogue["mode"] == "gate":
+            ep.mode = _lib.PK_EPI_GATE
+            args.y_batch_stride, args.y_ld = T * y_split.hi.stride(1), y_split.hi.stride(1)
+            res = epilogue.get("residual")
+            if res is not None:
+                assert res.dtype == torch.float32 and res.stride(-1) == 1 and res.shape[0] == B and res.shape[1] == T
+                ep.residual, ep.residual_batch_stride, ep.residual_ld = res.data_ptr(), res.stride(0), res.stride(1)
+        else:
+            ep.mode = _lib.PK_EPI_WF_UPDATE
+            state, skip = epilogue["state"], epilogue["skip"]
+            assert state.is_contiguous() and skip.is_contiguous() and tuple(state.shape) == (B, T, Cc) == tuple(skip.shape)
+            ep.state, ep.skip, ep.skip_init = state.data_ptr(), skip.data_ptr(), 1 if epilogue.get("skip_init") else 0
+            buf = epilogue.get("buf")
+            if buf is not None:
+                assert buf.hi.is_contiguous() and buf.hi.shape[0] == B and buf.hi.shape[1] == T
+                ep.buf_hi, ep.buf_lo, ep.buf_ld, ep.buf_col0 = buf.hi.data_ptr(), buf.lo.data_ptr(), buf.hi.stride(1), int(epilogue.get("buf_col0", 0))
+        _lib.check(_lib.lib().pk_conv_gemm_ex(C.byref(args), C.byref(ep), _stream()), "pk_conv_gemm_ex")
+        return None, y_split
     fn = _lib.lib().pk_conv_gemm_simt if simt else _lib.lib().pk_conv_gemm
     _lib.check(fn(C.byref(args), _stream()), "pk_conv_gemm")
     return y_f32, y_split
