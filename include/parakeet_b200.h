@@ -198,7 +198,7 @@ int pk_pwg_tail(const float* skip, const float* skip_bias, const float* w1, cons
                 float scale, int64_t rows, float* out, pk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * FastSpeech2 row-wise kernels (reference: parakeet/models/fastspeech2/fastspeech2.py and parakeet/modules/*).
+ * FastSpeech2 row-wise kernels (reference: parakeet/models/fastspeech2/fastspeech2.py and the files under parakeet/modules).
  * Shapes are (batch, t, channels) channels-last fp32 unless noted.  `lens` (device int32 [batch] or NULL) selects
  * the "independent utterances" mode used for batched inference: rows t >= lens[b] are written as zero so that every
  * utterance sees exactly the zero padding it would see alone; with lens == NULL padded rows are computed like any

@@ -1,1 +1,2 @@
 from .fs2_step import FastSpeech2TrainStep  # noqa: F401
+from .flat import FlatBuffers  # noqa: F401

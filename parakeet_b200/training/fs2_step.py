@@ -21,6 +21,7 @@ import torch.distributed as dist
 from .. import _lib, ops
 from ..models.fastspeech2 import FastSpeech2, _i32
 from ..ops import Split, _ptr, _stream
+from .flat import FlatBuffers
 
 BUFFERS = ("_mean", "_variance")
 
@@ -53,21 +54,10 @@ class FastSpeech2TrainStep:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         dev = model.device
         names = [k for k in model._params if not k.endswith(BUFFERS)]
-        sizes = [model._params[k].numel() for k in names]
-        offs, tot = [], 0
-        for s in sizes:
-            offs.append(tot)
-            tot += (s + 3) // 4 * 4                      # keep every view 16-byte aligned
-        self.flat = torch.zeros(tot, dtype=torch.float32, device=dev)
-        self.gflat = torch.zeros(tot, dtype=torch.float32, device=dev)
-        self.adam_m = torch.zeros(tot, dtype=torch.float32, device=dev)
-        self.adam_v = torch.zeros(tot, dtype=torch.float32, device=dev)
-        self.grads = {}
-        for k, o, s in zip(names, offs, sizes):
-            shape = model._params[k].shape
-            self.flat[o:o + s].copy_(model._params[k].reshape(-1))
-            model._params[k] = self.flat[o:o + s].view(shape)      # the model now reads the flat buffer
-            self.grads[k] = self.gflat[o:o + s].view(shape)
+        self.buffers = FlatBuffers(model._params, names, dev)      # the model's tensors become views of one flat buffer
+        self.flat, self.gflat, self.grads = self.buffers.flat, self.buffers.gflat, self.buffers.grads
+        self.adam_m = torch.zeros(self.buffers.total, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(self.buffers.total, dtype=torch.float32, device=dev)
         model._packed = None
         self.step_count = 0
         self.sums = torch.zeros(4096, dtype=torch.float32, device=dev)
@@ -401,7 +391,7 @@ class FastSpeech2TrainStep:
         """One update: returns the four loss values (device tensor: l1, duration, pitch, energy)."""
         losses = self.forward_backward(batch)
         if self.world > 1:
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)      # the one exchange step of the path
+            self.buffers.all_reduce_grads(self.group)                                # the one exchange step of the path
         self.step_count += 1
         _lib.check(_lib.lib().pk_adam(_ptr(self.flat), _ptr(self.gflat), _ptr(self.adam_m), _ptr(self.adam_v), self.flat.numel(),
                                       self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0 / self.world, _stream()), "pk_adam")

@@ -95,3 +95,35 @@ def test_polyphase_table_equals_stretch_then_fir():
         xp = np.pad(x, (1, 1))
         out = np.array([sum(poly[k, t % s] * xp[t // s + k] for k in range(3)) for t in range(s * len(x))])
         assert np.allclose(out, ref, atol=1e-5)
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/parakeet_b200.h must compile as C (it is what a cgo / ctypes / cffi binding consumes) and the ctypes mirrors in
+    parakeet_b200/_lib.py must have the C compiler's field offsets and sizes."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"pk_operand": _lib.Operand, "pk_conv_gemm_args": _lib.ConvGemmArgs, "pk_pwg_layer_args": _lib.PwgLayerArgs,
+               "pk_gemm_epilogue": _lib.GemmEpilogue}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "parakeet_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = mirrors[cname]
+        expect = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == expect, (cname, field, value, expect)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
