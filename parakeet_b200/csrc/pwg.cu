@@ -1200,7 +1200,7 @@ extern "C" int pk_pwg_residual_layer(const pk_pwg_layer_args* a, pk_stream_t str
   CUtensorMap tx_hi, tx_lo, tc_hi, tc_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
   int rc;
   const uint64_t T = a->t, B = a->batch;
-  // CTA-pair kernel (weights resident, half per CTA) unless the device has an odd SM count or PK_PWG_PAIR=0
+  // CTA-pair kernel (weights resident, half per CTA) unless PK_PWG_PAIR=0
   static const bool use_pair = []() {
     const char* e = getenv("PK_PWG_PAIR");
     return !(e && e[0] == '0') && sm_count() >= 2;
