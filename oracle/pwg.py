@@ -176,3 +176,73 @@ def synth_inputs(seed=2, batch=32, mel_frames=400, cfg=None):
     c = F.pad(mel, (w, w), mode="replicate")
     x = torch.randn(batch, cfg["in_channels"], mel_frames * hop, generator=g)
     return x, c
+
+
+# ----------------------------------------------------------------------------------------
+# Discriminator and the GAN training step (SURVEY.md 8f.1 - the "next" row after the generator forward).
+# ----------------------------------------------------------------------------------------
+DEFAULT_DISCRIMINATOR_PARAMS = dict(  # examples/GANVocoder/parallelwave_gan/baker/conf/default.yaml:50-60
+    in_channels=1, out_channels=1, kernel_size=3, layers=10, conv_channels=64, dilation_factor=1, bias=True,
+    nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.2}, use_weight_norm=True)
+
+
+def discriminator_dilations(cfg=None):
+    """Dilation of conv i (parallel_wavegan.py:571-576): 1 for i = 0, else i (dilation_factor 1) or factor**i; last conv 1."""
+    cfg = {**DEFAULT_DISCRIMINATOR_PARAMS, **(cfg or {})}
+    f = cfg["dilation_factor"]
+    return [1 if i == 0 else (i if f == 1 else f ** i) for i in range(cfg["layers"] - 1)] + [1]
+
+
+def discriminator_forward(params, x, cfg=None):
+    """PWGDiscriminator.forward (parallel_wavegan.py:554-614): (N, 1, T) audio -> (N, 1, T) logits.
+    layers-1 x [Conv1D(k, dilation d_i, 'same' zero padding) + LeakyReLU(0.2)] + Conv1D(k); weights folded (w = g v/|v|)."""
+    cfg = {**DEFAULT_DISCRIMINATOR_PARAMS, **(cfg or {})}
+    k = cfg["kernel_size"]
+    slope = cfg["nonlinear_activation_params"]["negative_slope"]
+    dil = discriminator_dilations(cfg)
+    n = cfg["layers"]
+    for i in range(n):
+        pre = f"conv_layers.{2 * i}."                                  # Sequential index: conv at 2i, activation at 2i+1
+        x = F.conv1d(x, params[pre + "weight"], params.get(pre + "bias"), padding=(k - 1) // 2 * dil[i], dilation=dil[i])
+        if i < n - 1:
+            x = F.leaky_relu(x, slope)
+    return x
+
+
+def synth_discriminator_params(seed=12, cfg=None):
+    cfg = {**DEFAULT_DISCRIMINATOR_PARAMS, **(cfg or {})}
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    cin = cfg["in_channels"]
+    for i in range(cfg["layers"]):
+        cout = cfg["out_channels"] if i == cfg["layers"] - 1 else cfg["conv_channels"]
+        bound = 1.7 / math.sqrt(cin * cfg["kernel_size"])
+        p[f"conv_layers.{2 * i}.weight"] = (torch.rand(cout, cin, cfg["kernel_size"], generator=g) * 2 - 1) * bound
+        p[f"conv_layers.{2 * i}.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+        cin = cfg["conv_channels"]
+    return p
+
+
+def gan_step_losses(gen_params, dis_params, noise, mel, wav, adversarial=True, lambda_adv=4.0, gen_cfg=None, dis_cfg=None):
+    """PWGUpdater.update_core (parallel_wavegan_updater.py:76-153) as two differentiable scalars.
+
+    generator loss  = sc + mag (MultiResolutionSTFTLoss of G(noise, mel) vs wav) [+ lambda_adv * MSE(D(G(.)), 1)]
+    discriminator loss = MSE(D(wav), 1) + MSE(D(G(.).detach()), 0)            (only once the discriminator trains)
+    wav, noise: (B, 1, T); mel: (B, 80, T' + 2w).  Returns a dict of tensors (call .backward() on the two losses)."""
+    from . import stft as ostft
+    wav_ = generator_forward(gen_params, noise, mel, gen_cfg)
+    sc, mag = ostft.multi_resolution_stft_loss(wav_.squeeze(1), wav.squeeze(1))
+    out = dict(wav_=wav_, spectral_convergence_loss=sc, log_stft_magnitude_loss=mag)
+    gen_loss = sc + mag
+    if adversarial:
+        p_ = discriminator_forward(dis_params, wav_, dis_cfg)
+        adv = F.mse_loss(p_, torch.ones_like(p_))
+        out["adversarial_loss"] = adv
+        gen_loss = gen_loss + lambda_adv * adv
+        p = discriminator_forward(dis_params, wav, dis_cfg)
+        pf = discriminator_forward(dis_params, wav_.detach(), dis_cfg)
+        out["real_loss"] = F.mse_loss(p, torch.ones_like(p))
+        out["fake_loss"] = F.mse_loss(pf, torch.zeros_like(pf))
+        out["discriminator_loss"] = out["real_loss"] + out["fake_loss"]
+    out["generator_loss"] = gen_loss
+    return out

@@ -159,3 +159,39 @@ def test_waveflow_flow_forward_inverse_identity():
         x_back = owf.flow_inverse(p, "decoder.0.", z, cond, 8, 16)
     assert logs.abs().max() > 1e-3                      # the flow is not the identity
     assert (x_back - x).abs().max().item() < 1e-4
+
+
+def test_pwg_discriminator_matches_module_restatement_and_gan_step_differentiates():
+    """SURVEY 8f.1 groundwork: the discriminator restatement against torch.nn modules carrying the same weights, the
+    dilation rule of parallel_wavegan.py:571-576, and the two losses of PWGUpdater.update_core being differentiable."""
+    import torch.nn as nn
+    from oracle import pwg as opwg
+    assert opwg.discriminator_dilations() == [1, 1, 2, 3, 4, 5, 6, 7, 8, 1]
+    dp = opwg.synth_discriminator_params(12)
+    mods, cin = [], 1
+    for i, d in enumerate(opwg.discriminator_dilations()):
+        cout = 1 if i == 9 else 64
+        c = nn.Conv1d(cin, cout, 3, padding=d, dilation=d)
+        c.weight.data.copy_(dp[f"conv_layers.{2 * i}.weight"]); c.bias.data.copy_(dp[f"conv_layers.{2 * i}.bias"])
+        mods.append(c)
+        if i < 9:
+            mods.append(nn.LeakyReLU(0.2))
+        cin = 64
+    x = torch.randn(2, 1, 600, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.allclose(opwg.discriminator_forward(dp, x), nn.Sequential(*mods)(x), atol=1e-6)
+    cfg = dict(layers=4, stacks=2, upsample_scales=[2, 3])                  # small generator: hop 6
+    gp = {k: v.clone().requires_grad_(True) for k, v in opwg.fold_weight_norm(opwg.synth_params(2, cfg, weight_norm=True)).items()}
+    dq = {k: v.clone().requires_grad_(True) for k, v in dp.items()}
+    g = torch.Generator().manual_seed(3)
+    mel = torch.randn(2, 80, 500 + 4, generator=g); noise = torch.randn(2, 1, 3000, generator=g); wav = torch.randn(2, 1, 3000, generator=g) * 0.1
+    out = opwg.gan_step_losses(gp, dq, noise, mel, wav, gen_cfg=cfg)
+    out["generator_loss"].backward(retain_graph=True)
+    no_grad = [k for k, v in gp.items() if v.grad is None]
+    assert all(k.startswith("conv_layers.3.conv1x1_out") for k in no_grad)   # the last block's residual output is unused (:469)
+    assert all(torch.isfinite(v.grad).all() and float(v.grad.abs().sum()) > 0 for v in gp.values() if v.grad is not None)
+    for v in dq.values():
+        v.grad = None
+    out["discriminator_loss"].backward()
+    assert all(torch.isfinite(v.grad).all() and float(v.grad.abs().sum()) > 0 for v in dq.values())
+    assert float(out["generator_loss"].detach()) > float((out["spectral_convergence_loss"] + out["log_stft_magnitude_loss"]).detach()) - 1e-6
