@@ -195,3 +195,62 @@ def test_pwg_discriminator_matches_module_restatement_and_gan_step_differentiate
     out["discriminator_loss"].backward()
     assert all(torch.isfinite(v.grad).all() and float(v.grad.abs().sum()) > 0 for v in dq.values())
     assert float(out["generator_loss"].detach()) > float((out["spectral_convergence_loss"] + out["log_stft_magnitude_loss"]).detach()) - 1e-6
+
+
+def test_adam_restatement_equals_torch_adam():
+    """Paddle's Adam form (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), eps scaled by sqrt(1-b2^t)) is algebraically torch.optim.Adam:
+    an independent implementation of the optimiser the training step is checked against."""
+    from oracle.fastspeech2 import adam_step
+    g = torch.Generator().manual_seed(7)
+    p0 = {"w": torch.randn(6, 5, generator=g), "b": torch.randn(5, generator=g)}
+    tp = {k: v.clone().requires_grad_(True) for k, v in p0.items()}
+    opt = torch.optim.Adam(list(tp.values()), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p, state = {k: v.clone() for k, v in p0.items()}, {}
+    for step in range(4):
+        grads = {k: torch.randn(v.shape, generator=g) * (10.0 ** -step) for k, v in p0.items()}
+        for k in tp:
+            tp[k].grad = grads[k].clone()
+        opt.step()
+        p = adam_step(p, grads, state, 1e-3, 0.9, 0.999, 1e-8)
+        for k in p:
+            assert torch.allclose(p[k], tp[k].detach(), atol=1e-7, rtol=1e-6), (step, k)
+
+
+def test_weight_norm_fold_equals_torch_weight_norm_and_train_bn_equals_torch_batch_norm():
+    """w = g * v / ||v|| over all dims but the first (paddle weight_norm dim 0) against torch's own weight_norm; the
+    train-mode BatchNorm normalisation against torch.nn.BatchNorm1d (the running variance differs by design: Paddle keeps the
+    biased batch variance, torch the unbiased one - SURVEY 8a hazards)."""
+    import torch.nn as nn
+    from oracle import fastspeech2 as ofs
+    from oracle import pwg as opwg
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                     # torch deprecates this spelling; it is the reference's semantics
+        conv = nn.utils.weight_norm(nn.Conv1d(5, 7, 3), dim=0)
+    with torch.no_grad():
+        conv.weight_g.mul_(torch.rand(7, 1, 1) + 0.5)
+    folded = opwg.fold_weight_norm({"c.weight_g": conv.weight_g.detach().reshape(-1), "c.weight_v": conv.weight_v.detach(),
+                                    "c.bias": conv.bias.detach()})
+    x = torch.randn(2, 5, 11)
+    with torch.no_grad():
+        assert torch.allclose(torch.nn.functional.conv1d(x, folded["c.weight"], folded["c.bias"]), conv(x), atol=1e-6)
+    # one postnet layer in train mode
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(6, 4, 5, generator=g) * 0.3
+    p = {"postnet.postnet.0.0.weight": w, "postnet.postnet.0.1.weight": torch.rand(6, generator=g) + 0.5,
+         "postnet.postnet.0.1.bias": torch.randn(6, generator=g), "postnet.postnet.0.1._mean": torch.randn(6, generator=g),
+         "postnet.postnet.0.1._variance": torch.rand(6, generator=g) + 0.5}
+    xs = torch.randn(3, 4, 20, generator=g)
+    stats = {}
+    y = ofs.postnet(p, xs, 1, train_bn=True, new_stats=stats)
+    bn = nn.BatchNorm1d(6, eps=1e-5, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(p["postnet.postnet.0.1.weight"]); bn.bias.copy_(p["postnet.postnet.0.1.bias"])
+        bn.running_mean.copy_(p["postnet.postnet.0.1._mean"]); bn.running_var.copy_(p["postnet.postnet.0.1._variance"])
+        h = torch.nn.functional.conv1d(xs, w, None, padding=2)
+        ref = bn.train()(h)
+    assert torch.allclose(y, ref, atol=1e-5)
+    assert torch.allclose(stats["postnet.postnet.0.1._mean"], bn.running_mean, atol=1e-6)
+    n = h.numel() // 6
+    biased = (bn.running_var - 0.9 * p["postnet.postnet.0.1._variance"]) * (n - 1) / n + 0.9 * p["postnet.postnet.0.1._variance"]
+    assert torch.allclose(stats["postnet.postnet.0.1._variance"], biased, atol=1e-6)
