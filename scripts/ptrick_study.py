@@ -82,3 +82,63 @@ for m0 in range(0, T, 128):
     cols = nz[rows].any(0).nonzero().flatten()
     worst = max(worst, int(cols.max() - cols.min() + 1))
 print("frames touched by one 128-sample tile (K of the aux chunk):", worst)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Band tables a kernel can consume: row t of U for an utterance of F frames, as K = 8 coefficients starting at frame
+# j0(t) = t // hop - 2, assembled from three small tables (interior period, first tile(s), last tile(s)).
+# ----------------------------------------------------------------------------------------------------------------
+K = 8
+EDGE = 128          # rows nearest to either end that get their own coefficients (edge effects reach 95 samples)
+
+
+def band_rows(Umat):
+    Tn, Fn = Umat.shape
+    rows = torch.zeros(Tn, K, dtype=Umat.dtype)
+    for t in range(Tn):
+        j0 = t // hop - 2
+        for k in range(K):
+            j = j0 + k
+            if 0 <= j < Fn:
+                rows[t, k] = Umat[t, j]
+        # everything outside the window must be zero
+        lo, hi = max(j0, 0), min(j0 + K, Fn)
+        assert Umat[t, :lo].abs().max() == 0 if lo > 0 else True
+        assert Umat[t, hi:].abs().max() == 0 if hi < Fn else True
+    return rows
+
+
+def build_tables(frames_ref=12):
+    B_ = band_rows(upsample_matrix(frames_ref))
+    Tn = frames_ref * hop
+    mid = (frames_ref // 2) * hop
+    return dict(interior=B_[mid:mid + hop].clone(), begin=B_[:EDGE].clone(), end=B_[Tn - EDGE:].clone())
+
+
+def assemble(tables, frames):
+    Tn = frames * hop
+    rows = torch.empty(Tn, K, dtype=torch.float64)
+    for t in range(Tn):
+        if t < EDGE:
+            rows[t] = tables["begin"][t]
+        elif t >= Tn - EDGE:
+            rows[t] = tables["end"][t - (Tn - EDGE)]
+        else:
+            rows[t] = tables["interior"][t % hop]
+    return rows
+
+
+tabs = build_tables()
+for frames in (3, 4, 7, 24):
+    want = band_rows(upsample_matrix(frames))
+    got = assemble(tabs, frames)
+    # near the start the window is clipped at frame 0 / near the end at frame F-1: clipped entries are multiplied by
+    # out-of-range (zero) rows of P in the kernel (TMA zero fill), so compare only in-range entries
+    Tn = frames * hop
+    ok = True
+    for t in range(Tn):
+        j0 = t // hop - 2
+        for k in range(K):
+            if 0 <= j0 + k < frames and want[t, k] != got[t, k]:
+                ok = False
+    print(f"frames {frames:3d}: U rebuilt from (interior[{hop}], begin[{EDGE}], end[{EDGE}]) tables bit-exactly: {ok}")
