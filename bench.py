@@ -338,7 +338,7 @@ def main():
             torch.cuda.synchronize()
             wf_ms = e0.elapsed_time(e1) / 3
             out["extra"]["waveflow_b16_c64"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
-                                                "note": "cfg4; one CUDA graph of 5 040 kernel nodes per call"}
+                                                "note": "cfg4; one CUDA graph of ~2 300 kernel nodes per call (fused GEMM epilogues)"}
         except Exception as ex:  # extras must never break the headline line
             out.setdefault("extra", {})["error"] = repr(ex)
     if not args.no_extra and world == 1:
