@@ -1,0 +1,64 @@
+"""Frame-rate conditioning for the Parallel WaveGAN residual stack (experimental, PK_PWG_FRAME_COND=1).
+
+The upsampling network of ConvInUpsampleNet (parallel_wavegan.py:119-138,201-216) is linear and acts on every channel
+alike, so the 1x1 aux convolution of a residual block (:300-303) commutes with it:
+
+    conv1x1_aux(upsample(m'))[t, n] = sum_j U[t, j] * P[j, n],        m' = conv_in(mel),  P = W_aux m'   (frame rate)
+
+U (T x frames) is banded: row t has at most 4 non-zero frames starting at t // hop - 2, it repeats with period hop away from
+the ends of the utterance, and the zero-padding of the FIR stages only changes rows within 95 samples of either end
+(scripts/ptrick_study.py).  A 128-sample tile starting at t0 therefore needs the K = 16 frames j0 .. j0 + 15,
+j0 = t0 // hop - 2, and its A operand is the "tile-relative band table": row t holds U[t, j0(tile of t) + k], k < 16.
+This module builds that table on the host (constants of the model, computed once per utterance length); the layer kernel
+multiplies it with the matching window of P, frames outside [0, frames) reading as zero (TMA out-of-bounds fill).
+"""
+import torch
+import torch.nn.functional as F
+
+TILE = 128
+KWIN = 16
+EDGE = 128          # rows next to either end of an utterance that carry their own coefficients (edge effects reach < 128)
+
+
+def upsample_operator(firs, scales, frames):
+    """U (frames * hop, frames) in float64: column j = response of the stretch / FIR cascade to an impulse at frame j."""
+    x = torch.eye(frames, dtype=torch.float64)[None, None]            # (1, 1, frames 'channels', frames)
+    for fir, s in zip(firs, scales):
+        x = F.interpolate(x, scale_factor=(1, s), mode="nearest")      # Stretch2D (:48-63)
+        x = F.conv2d(x, fir.reshape(1, 1, 1, -1).to(torch.float64), padding=(0, s))
+    return x[0, 0].transpose(0, 1).contiguous()                        # (T, frames)
+
+
+def _row_windows(U, hop, width):
+    """rows[t, k] = U[t, t // hop - 2 + k] (zero outside the matrix); asserts that nothing lies outside the window."""
+    T, Fr = U.shape
+    t = torch.arange(T)
+    j = (t // hop - 2)[:, None] + torch.arange(width)[None, :]
+    ok = (j >= 0) & (j < Fr)
+    rows = torch.where(ok, U[t[:, None].expand_as(j), j.clamp(0, Fr - 1)], torch.zeros((), dtype=U.dtype))
+    assert torch.allclose(rows.sum(1), U.sum(1), atol=1e-12), "upsampling operator is wider than the K window"
+    return rows
+
+
+def tile_band_table(firs, scales, frames, width=8):
+    """(frames * hop, KWIN) float64: row t = U[t, j0 + k] with j0 = (t // TILE * TILE) // hop - 2 (tile-relative window)."""
+    hop = 1
+    for s in scales:
+        hop *= s
+    T = frames * hop
+    ref_frames = 8
+    if frames <= ref_frames or T < 2 * EDGE + hop:
+        rows = _row_windows(upsample_operator(firs, scales, frames), hop, width)
+    else:
+        ref = _row_windows(upsample_operator(firs, scales, ref_frames), hop, width)
+        mid = (ref_frames // 2) * hop
+        t = torch.arange(T)
+        rows = ref[mid + t % hop]                                       # interior: period hop
+        rows[:EDGE] = ref[:EDGE]
+        rows[T - EDGE:] = ref[ref_frames * hop - EDGE:]
+    t = torch.arange(T)
+    shift = (t // hop - 2) - ((t // TILE * TILE) // hop - 2)            # 0 or 1 (a tile is shorter than a hop)
+    assert int(shift.max()) + width <= KWIN
+    out = torch.zeros(T, KWIN, dtype=torch.float64)
+    out.scatter_(1, shift[:, None] + torch.arange(width)[None, :], rows)
+    return out

@@ -254,3 +254,35 @@ def test_weight_norm_fold_equals_torch_weight_norm_and_train_bn_equals_torch_bat
     n = h.numel() // 6
     biased = (bn.running_var - 0.9 * p["postnet.postnet.0.1._variance"]) * (n - 1) / n + 0.9 * p["postnet.postnet.0.1._variance"]
     assert torch.allclose(stats["postnet.postnet.0.1._variance"], biased, atol=1e-6)
+
+
+def test_pwg_frame_rate_conditioning_tables_reproduce_the_aux_path():
+    """DESIGN 7.2 groundwork: conv1x1_aux(upsample(m')) == band_table_tile @ (W_aux m')[window], tile by tile, with exactly the
+    index conventions the layer kernel will use (window start t0 // hop - 2, frames outside [0, frames) read as zero)."""
+    from oracle import pwg as opwg
+    from parakeet_b200.models import _pwg_frame_cond as fc
+    cfg = opwg.DEFAULT_GENERATOR_PARAMS
+    scales = cfg["upsample_scales"]
+    hop = 300
+    params = {k: v.double() for k, v in opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True)).items()}
+    firs = [params[f"upsample_net.upsample.up_layers.{2 * i + 1}.weight"].reshape(-1) for i in range(len(scales))]
+    w_aux = params["conv_layers.11.conv1x1_aux.weight"][:, :, 0]                       # (128, 80)
+    g = torch.Generator().manual_seed(0)
+    for frames in (1, 2, 3, 9, 21):
+        mel = torch.randn(1, 80, frames + 4, generator=g, dtype=torch.float64)
+        m1 = torch.nn.functional.conv1d(mel, params["upsample_net.conv_in.weight"])     # (1, 80, frames)
+        c_up = opwg.upsample_net(params, m1, scales)[0]                                # (80, T)
+        ref = (w_aux @ c_up).transpose(0, 1)                                           # (T, 128)
+        P = (w_aux @ m1[0]).transpose(0, 1)                                            # (frames, 128)
+        table = fc.tile_band_table(firs, scales, frames)
+        T = frames * hop
+        assert table.shape == (T, fc.KWIN)
+        Ppad = torch.zeros(frames + 2 * fc.KWIN, 128, dtype=torch.float64)
+        Ppad[fc.KWIN:fc.KWIN + frames] = P
+        worst = 0.0
+        for t0 in range(0, T, fc.TILE):
+            j0 = t0 // hop - 2
+            win = Ppad[fc.KWIN + j0:fc.KWIN + j0 + fc.KWIN]                           # zero outside [0, frames)
+            got = table[t0:t0 + fc.TILE] @ win
+            worst = max(worst, float((got - ref[t0:t0 + fc.TILE]).abs().max()))
+        assert worst < 1e-12 * max(1.0, float(ref.abs().max())), (frames, worst)
