@@ -189,6 +189,40 @@ typedef struct pk_pwg_layer_args {
 } pk_pwg_layer_args;
 int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
 
+/* EXPERIMENTAL (not used by default; PK_PWG_FRAME_COND=1 in the Python model): pk_pwg_residual_layer with frame-rate
+ * conditioning.  The upsampling network is linear and per channel, so conv1x1_aux(upsample(m'))[t, n] =
+ * sum_j U[t, j] * P[j, n] with P = conv1x1_aux applied to m' = conv_in(mel) at FRAME rate.  Instead of the sample-rate
+ * conditioning planes the kernel takes
+ *   u_hi / u_lo: the tile-relative band table of U as split planes (u_batches, t, 64): row t holds U[t, j0 + k] in column
+ *                k < 16 (zeros after), j0 = ((t / 128) * 128) / hop - 2; u_batches = 1 (shared) or batch;
+ *   p_hi / p_lo: P as split planes (batch, p_rows, p_ld) with frames along the last axis (p_frames valid columns); this
+ *                layer's 128 output channels are rows [p_row0, p_row0 + 128).
+ * w1 / w2 / bias1 / bias2 / skip / lens as in pk_pwg_layer_args (the aux columns of w1 are not read).  hop >= 128. */
+typedef struct pk_pwg_layer_fc_args {
+  int32_t batch, t, dilation, hop;
+  const int32_t* lens;
+  const void* x_hi;
+  const void* x_lo;
+  void* y_hi;
+  void* y_lo;
+  const void* u_hi;
+  const void* u_lo;
+  int32_t u_batches;
+  int32_t p_rows, p_ld, p_frames, p_row0;
+  const void* p_hi;
+  const void* p_lo;
+  const void* w1_hi;
+  const void* w1_lo;
+  const void* w2_hi;
+  const void* w2_lo;
+  const float* bias1;      /* HOST pointers, as in pk_pwg_layer_args */
+  const float* bias2;
+  float* skip;
+  int32_t skip_init;
+  void* prof;
+} pk_pwg_layer_fc_args;
+int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* args, pk_stream_t stream);
+
 /* last_conv_layers (:429-440) on the scaled skip sum (:469-471):
  *   out[row] = w2 . relu(W1 relu((skip[row] + skip_bias) * scale) + b1) + b2
  * with skip fp32 (rows, 64), W1 [64 out][64 in], w2 [64]; out fp32 (rows).  skip_bias [64] (or NULL) is the sum of the

@@ -65,6 +65,15 @@ class PwgLayerArgs(C.Structure):
                 ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
 
 
+class PwgLayerFcArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("dilation", C.c_int32), ("hop", C.c_int32), ("lens", C.c_void_p),
+                ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("u_hi", C.c_void_p),
+                ("u_lo", C.c_void_p), ("u_batches", C.c_int32), ("p_rows", C.c_int32), ("p_ld", C.c_int32),
+                ("p_frames", C.c_int32), ("p_row0", C.c_int32), ("p_hi", C.c_void_p), ("p_lo", C.c_void_p),
+                ("w1_hi", C.c_void_p), ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p),
+                ("bias1", C.c_void_p), ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
+
+
 def _declare(L):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
@@ -77,6 +86,7 @@ def _declare(L):
         "pk_pwg_upsample": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
         "pk_pwg_first_conv": [vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
+        "pk_pwg_residual_layer_fc": [C.POINTER(PwgLayerFcArgs), vp],
         "pk_pwg_tail": [vp, vp, vp, vp, vp, vp, f32, i64, vp, vp],
         "pk_embed_pe": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],

@@ -1,0 +1,567 @@
+// pk_pwg_residual_layer_fc: the CTA-pair residual-layer kernel of pwg.cu with FRAME-RATE CONDITIONING (experimental, not
+// the default path; selected by the Python model with PK_PWG_FRAME_COND=1 - DESIGN.md 7.2).
+//
+// The upsampling network is linear and per channel, so conv1x1_aux(upsample(m'))[t, n] = sum_j U[t, j] (W_aux m')[j, n].
+// GEMM1's two conditioning K-chunks (80 channels of the 1.23 GB sample-rate conditioning tensor, 5 K-steps, 32 KB of
+// resident W_aux) become ONE K-step: A = the tile-relative band table of U (constants of the model,
+// models/_pwg_frame_cond.py), B = the 16-frame window of P = W_aux m' that the tile touches (frame rate, L2 resident).
+// Everything else - pipeline, barriers, gate, residual pass, stores - is the pair kernel of pwg.cu, copied so that the
+// default path stays untouched until this one has been validated on a GPU.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pk_host.h"
+#include "pk_sm100.cuh"
+
+namespace pk {
+namespace fc {
+
+constexpr int kPwgR = 64;
+constexpr int kPwgG = 128;
+constexpr int kPwgTile = 128 * kSwizzleBytes;
+constexpr int kPwgGateWarps = 4;
+constexpr int kPwgStoreWarps = 8;
+constexpr int kPwgFirstGateWarp = 4;
+constexpr int kPwgThreads = (kPwgFirstGateWarp + kPwgGateWarps + kPwgStoreWarps) * 32;
+constexpr int kFcG1Chunks = 4;                               // tap -d, tap +d, conditioning, centre tap
+constexpr int kFcStages = 3;
+constexpr int kFcStageBytes = 2 * kPwgTile;                  // A hi, A lo
+constexpr int kFcWTile = 64 * kSwizzleBytes;                 // 8 KB: 64 output channels x one K-chunk of one plane
+constexpr int kFcW1Bytes = 3 * 2 * kFcWTile;                 // 48 KB: three tap chunks
+constexpr int kFcW2Bytes = 2 * kFcWTile;                     // 16 KB
+constexpr int kFcPBytes = 2 * kFcWTile;                      // 16 KB: hi | lo of one P window
+constexpr int kFcSmem = kFcStages * kFcStageBytes + kFcW1Bytes + kFcW2Bytes + kFcWTile + 2 * kFcPBytes + 1024 + 256;
+
+struct FcLayerArgs {
+  int batch, t, dil, hop;
+  int u_bmul;                   // 0: one band table for all utterances, 1: one per utterance
+  int p_row0;                   // first row of this layer's 128 output channels in the P planes
+  const int32_t* lens;
+  float gate_c[128];
+  float out_b[64];
+  float k_a, k_g;
+  float* skip;
+  int skip_init;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  unsigned long long* prof;
+};
+
+#define PK_TICK(k)                                      \
+  if (kProf) {                                          \
+    const long long n_ = clock64();                     \
+    tacc[k] += n_ - tlast;                              \
+    tlast = n_;                                         \
+  }
+#define PK_TICK_FLUSH(base, n)                                                              \
+  if (kProf) {                                                                              \
+    for (int k_ = 0; k_ < (n); ++k_) atomicAdd(p.prof + (base) + k_, static_cast<unsigned long long>(tacc[k_])); \
+  }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+struct FcTileIter {   // 256-sample tiles of the pair; this CTA owns rows [m0 + 128 * rank, +128)
+  int idx, step, tiles_per_b, total, t;
+  const int32_t* lens;
+  __device__ FcTileIter(const FcLayerArgs& p)
+      : idx(static_cast<int>(blockIdx.x >> 1) - static_cast<int>(gridDim.x >> 1)), step(gridDim.x >> 1),
+        tiles_per_b((p.t + 255) >> 8), total(((p.t + 255) >> 8) * p.batch), t(p.t), lens(p.lens) {}
+  __device__ bool next(int& b, int& m0) {
+    for (;;) {
+      idx += step;
+      if (idx >= total) return false;
+      b = idx / tiles_per_b;
+      m0 = (idx % tiles_per_b) * 256;
+      const int len = lens ? min(__ldg(lens + b), t) : t;
+      if (m0 < len) return true;
+    }
+  }
+};
+
+template <bool kProf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwgThreads, 1)
+pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                      const __grid_constant__ CUtensorMap tm_u_hi, const __grid_constant__ CUtensorMap tm_u_lo,
+                    const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
+                      const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
+                      const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
+                      const FcLayerArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w1 = smem + kFcStages * kFcStageBytes;        // [chunk][hi | lo] 64-row tiles, resident
+  const uint32_t w2 = w1 + kFcW1Bytes;                         // [hi | lo]
+  const uint32_t ident = w2 + kFcW2Bytes;                      // this CTA's 64 rows of [0 | I]
+  const uint32_t pbuf = ident + kFcWTile;                      // [2][hi | lo] this CTA's 64 rows of the P window of a tile
+  const uint32_t bars = pbuf + 2 * kFcPBytes;
+  const uint32_t full_bar = bars;                              // [stages]   (leader's copy is the live one)
+  const uint32_t empty_bar = full_bar + 8 * kFcStages;         // [stages]
+  const uint32_t acc1_full = empty_bar + 8 * kFcStages;        // [2]
+  const uint32_t acc1_empty = acc1_full + 16;                  // [2] leader
+  const uint32_t acc2_full = acc1_empty + 16;                  // [2]
+  const uint32_t acc2_empty = acc2_full + 16;                  // [2] leader
+  const uint32_t z_full = acc2_empty + 16;                     // [2] leader
+  const uint32_t g2_free = z_full + 16;                        // [2]
+  const uint32_t w_bar = g2_free + 16;
+  const uint32_t tmem_slot = w_bar + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr float kLog2e = 1.4426950408889634f;
+  (void)kLog2e;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_u_hi); tma_prefetch_desc(&tm_u_lo); tma_prefetch_desc(&tm_p_hi); tma_prefetch_desc(&tm_p_lo);
+    tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w1_lo); tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo);
+    for (int s = 0; s < kFcStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, 2 * kPwgGateWarps);
+      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, 2 * kPwgStoreWarps);
+      mbar_init_a(z_full + 8 * i, 2 * kPwgGateWarps); mbar_init_a(g2_free + 8 * i, 1);
+    }
+    mbar_init_a(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm_a<512>(tmem_slot);
+  if (threadIdx.x >= 128 && threadIdx.x < 192) {
+    // this CTA's half of the B operand [0 | I] of the residual pass: rank 0 holds output columns 0..63 (all zero: the
+    // skip half starts from 0), rank 1 holds columns 64..127 (row n = e_n: out column n receives x[:, n])
+    const int n = threadIdx.x - 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (rank == 1 && (n >> 3) == c) {
+        const uint32_t one = (n & 1) ? 0x3f800000u : 0x00003f80u;
+        const int w = (n & 7) >> 1;
+        v.x = w == 0 ? one : 0; v.y = w == 1 ? one : 0; v.z = w == 2 ? one : 0; v.w = w == 3 ? one : 0;
+      }
+      sts_u4(ident + n * kSwizzleBytes + ((c ^ (n & 7)) * 16), v);
+    }
+    fence_proxy_async_all();
+  }
+  tcgen05_fence_before();
+  cluster_sync();                      // barriers of both CTAs are initialised before any remote arrive / TMA credit
+  tcgen05_fence_after();
+  if (warp == 0 && lane == 0) {
+    // resident weights: this CTA's 64 output channels of the three tap chunks of W1 and of W2, both planes
+    mbar_arrive_expect_tx_a(w_bar, kFcW1Bytes + kFcW2Bytes);
+    for (int j = 0; j < 3; ++j) {
+      tma_load_3d_a(w1 + j * 2 * kFcWTile, &tm_w1_hi, w_bar, j * kChunkK, 64 * rank, 0);
+      tma_load_3d_a(w1 + j * 2 * kFcWTile + kFcWTile, &tm_w1_lo, w_bar, j * kChunkK, 64 * rank, 0);
+    }
+    tma_load_3d_a(w2, &tm_w2_hi, w_bar, 0, 64 * rank, 0);
+    tma_load_3d_a(w2 + kFcWTile, &tm_w2_lo, w_bar, 0, 64 * rank, 0);
+    mbar_wait_a(w_bar, 0);
+  }
+  cluster_sync();                      // both halves of the weights are in place before the leader's first MMA
+  const uint32_t tmem_base = lds_u32(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer (both CTAs, own rows) ------------------------------
+      uint32_t it = 0;
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tlast = clock64();
+      const uint32_t full_leader = mapa_shared(full_bar, 0);
+      int n_g1 = 0;   // tiles whose GEMM1 chunks have been issued (parity selects the P-window buffer)
+      auto load_g1 = [&](int b, int m0) {
+        for (int j = 0; j < kFcG1Chunks; ++j, ++it) {
+          const int s = it % kFcStages;
+          PK_TICK(1)
+          mbar_wait_a(empty_bar + 8 * s, ((it / kFcStages) & 1) ^ 1);
+          PK_TICK(0)
+          const uint32_t st = smem + s * kFcStageBytes;
+          const uint32_t fb = full_leader + 8 * s;
+          // chunk order: tap -d, tap +d, conditioning, centre tap (last: it also feeds the residual pass)
+          if (j == 2) {
+            // conditioning as U (W_aux m'): A = tile-relative band table rows [m0, m0 + 128) (K window = 16 frames inside a
+            // 64-wide box), B = the same 16 frames of P for this CTA's 64 output channels; frames outside the utterance are
+            // out of bounds of the tensor map and read as zero
+            if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * (kFcStageBytes + kFcPBytes));
+            tma_load_3d_2sm_a(st, &tm_u_hi, fb, 0, m0, b * p.u_bmul);
+            tma_load_3d_2sm_a(st + kPwgTile, &tm_u_lo, fb, 0, m0, b * p.u_bmul);
+            const int j0 = m0 / p.hop - 2;
+            const uint32_t pb = pbuf + (n_g1 & 1) * kFcPBytes;
+            tma_load_3d_2sm_a(pb, &tm_p_hi, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
+            tma_load_3d_2sm_a(pb + kFcWTile, &tm_p_lo, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
+          } else {
+            if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kFcStageBytes);   // the A chunks of both CTAs
+            const int wj = j == 0 ? 0 : j == 1 ? 2 : 1;
+            const int row = m0 + (wj - 1) * p.dil;
+            tma_load_3d_2sm_a(st, &tm_x_hi, fb, 0, row, b);
+            tma_load_3d_2sm_a(st + kPwgTile, &tm_x_lo, fb, 0, row, b);
+          }
+        }
+        ++n_g1;
+      };
+      int n_g2 = 0;
+      auto load_g2 = [&]() {
+        const int s = it % kFcStages;
+        PK_TICK(1)
+        mbar_wait_a(empty_bar + 8 * s, ((it / kFcStages) & 1) ^ 1);
+        PK_TICK(0)
+        mbar_arrive_a(g2_free + 8 * (n_g2 & 1));   // own gate warps may write z of this tile into the stage
+        ++n_g2;
+        if (leader) mbar_arrive_a(full_bar + 8 * s);   // no TMA in this slot; keeps the stage ring's phases uniform
+        ++it;
+      };
+      FcTileIter ti(p);
+      int b, m0, nb, nm0;
+      bool have = ti.next(b, m0);
+      if (have) load_g1(b, m0 + 128 * rank);
+      while (have) {
+        const bool have_next = ti.next(nb, nm0);
+        if (have_next) load_g1(nb, nm0 + 128 * rank);
+        load_g2();
+        have = have_next; b = nb; m0 = nm0;
+      }
+      PK_TICK(1)
+      if (leader) { PK_TICK_FLUSH(0, 2) }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16_f32(256, 128);
+      uint32_t it = 0;
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long tlast = clock64();
+      auto mma_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int ksteps, bool first) {
+        const uint64_t a_hi = make_smem_desc_sw128(a_addr), a_lo = make_smem_desc_sw128(a_addr + kPwgTile);
+        const uint64_t b_hi = make_smem_desc_sw128(b_addr), b_lo = make_smem_desc_sw128(b_addr + kFcWTile);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+          umma_bf16_2sm(d_tmem, a_hi + koff, b_hi + koff, idesc, !(first && k == 0));
+          umma_bf16_2sm(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+          umma_bf16_2sm(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+        }
+      };
+      auto g1 = [&](int i) {
+        const int buf = i & 1;
+        PK_TICK(6)
+        mbar_wait_a(acc1_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+        PK_TICK(0)
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + buf * 128;
+        for (int j = 0; j < kFcG1Chunks; ++j, ++it) {
+          const int s = it % kFcStages;
+          PK_TICK(2)
+          mbar_wait_a(full_bar + 8 * s, (it / kFcStages) & 1);
+          PK_TICK(1)
+          tcgen05_fence_after();
+          const uint32_t st = smem + s * kFcStageBytes;
+          if (j == 2) {
+            mma_chunk(d, st, pbuf + (i & 1) * kFcPBytes, 1, false);     // one K-step: 16 frames of band table x P window
+          } else {
+            const int wj = j == 0 ? 0 : j == 1 ? 2 : 1;
+            mma_chunk(d, st, w1 + wj * 2 * kFcWTile, 4, j == 0);
+          }
+          if (j == kFcG1Chunks - 1) {
+            // residual pass: acc2(i) = [0 | x_hi + x_lo] from the centre-tap tiles of both CTAs
+            PK_TICK(2)
+            mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+            PK_TICK(4)
+            tcgen05_fence_after();
+            const uint64_t a_hi = make_smem_desc_sw128(st), a_lo = make_smem_desc_sw128(st + kPwgTile);
+            const uint64_t b_id = make_smem_desc_sw128(ident);
+            const uint32_t d2 = tmem_base + 256 + buf * 128;
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+              umma_bf16_2sm(d2, a_hi + koff, b_id + koff, idesc, k != 0);
+              umma_bf16_2sm(d2, a_lo + koff, b_id + koff, idesc, 1);
+            }
+          }
+          umma_commit_2sm_a(empty_bar + 8 * s);
+        }
+        umma_commit_2sm_a(acc1_full + 8 * buf);
+      };
+      auto g2 = [&](int i) {
+        const int buf = i & 1;
+        const int s = it % kFcStages;
+        PK_TICK(2)
+        mbar_wait_cluster_a(z_full + 8 * (i & 1), (i >> 1) & 1);   // the gate warps of both CTAs wrote z into stage s
+        PK_TICK(3)
+        mbar_wait_a(full_bar + 8 * s, (it / kFcStages) & 1);
+        PK_TICK(5)
+        tcgen05_fence_after();
+        mma_chunk(tmem_base + 256 + buf * 128, smem + s * kFcStageBytes, w2, 4, false);
+        umma_commit_2sm_a(empty_bar + 8 * s);
+        umma_commit_2sm_a(acc2_full + 8 * buf);
+        ++it;
+      };
+      FcTileIter ti(p);
+      int b, m0;
+      int n_issued = 0, n_done = 0;
+      bool have = ti.next(b, m0);
+      if (have) g1(n_issued++);
+      while (have) {
+        const bool have_next = ti.next(b, m0);
+        if (have_next) g1(n_issued++);
+        g2(n_done++);
+        have = have_next;
+      }
+      PK_TICK(6)
+      PK_TICK_FLUSH(8, 7)
+      if (kProf) atomicAdd(p.prof + 32, static_cast<unsigned long long>(n_done));
+    }
+  } else if (warp < kPwgFirstGateWarp) {
+    // idle warps
+  } else if (warp < kPwgFirstGateWarp + kPwgGateWarps) {
+    // ------------------------------ gate warps (both CTAs, own TMEM lanes) ------------------------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t acc1_empty_l = mapa_shared(acc1_empty, 0), z_full_l = mapa_shared(z_full, 0);
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+    float k_a, k_g;
+    asm volatile("mov.f32 %0, %2;\n\tmov.f32 %1, %3;" : "=f"(k_a), "=f"(k_g) : "f"(p.k_a), "f"(p.k_g));
+    uint32_t it = kFcG1Chunks;
+    FcTileIter ti(p);
+    int b, m0, nb, nm0;
+    bool have = ti.next(b, m0);
+    for (int i = 0; have; ++i) {
+      const bool have_next = ti.next(nb, nm0);
+      if (have_next) it += kFcG1Chunks;
+      const uint32_t st2 = smem + (it % kFcStages) * kFcStageBytes;
+      ++it;
+      const int buf = i & 1;
+      PK_TICK(6)
+      mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
+      PK_TICK(0)
+      tcgen05_fence_after();
+      uint32_t zh[32], zl[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float va[32], vb[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + half * 32, va);
+        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
+        tmem_ld_wait();
+        if (half == 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed_a(acc1_empty_l + 8 * buf);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float z[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float e1 = ex2_approx(fminf(fmaf(va[j + e], k_a, p.gate_c[half * 32 + j + e]), 60.f));
+            const float e2 = ex2_approx(fmaf(vb[j + e], k_g, p.gate_c[64 + half * 32 + j + e]));
+            const float t1 = 1.f + e1;
+            z[e] = (1.f - e1) * rcp_approx(fmaf(t1, e2, t1));
+          }
+          split2(z[0], z[1], zh[half * 16 + j / 2], zl[half * 16 + j / 2]);
+          split2(z[2], z[3], zh[half * 16 + j / 2 + 1], zl[half * 16 + j / 2 + 1]);
+        }
+      }
+      PK_TICK(1)
+      mbar_wait_a(g2_free + 8 * (i & 1), (i >> 1) & 1);
+      PK_TICK(2)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int chunk = q ^ (r & 7);
+        sts_u4(st2 + r * kSwizzleBytes + chunk * 16, make_uint4(zh[4 * q], zh[4 * q + 1], zh[4 * q + 2], zh[4 * q + 3]));
+        sts_u4(st2 + kPwgTile + r * kSwizzleBytes + chunk * 16, make_uint4(zl[4 * q], zl[4 * q + 1], zl[4 * q + 2], zl[4 * q + 3]));
+      }
+      fence_proxy_async_smem();          // z lives in this CTA's smem and is read by this CTA's tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_a(z_full_l + 8 * (i & 1));
+      PK_TICK(3)
+      have = have_next; b = nb; m0 = nm0;
+    }
+    PK_TICK(6)
+    if (lane == 0 && quarter == 0 && leader) { PK_TICK_FLUSH(16, 7) }
+  } else {
+    // ------------------------------ store warps (both CTAs) ------------------------------
+    const int sw = warp - kPwgFirstGateWarp - kPwgGateWarps;
+    const int quarter = warp & 3;
+    const int half = sw >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t acc2_empty_l = mapa_shared(acc2_empty, 0);
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+    FcTileIter ti(p);
+    int b, m0;
+    bool have = ti.next(b, m0);
+    if (half == 0) {
+      for (int i = 0; have; ++i) {
+        const int buf = i & 1;
+        const int tt = m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
+        float* dst = p.skip + (static_cast<long long>(b) * p.t + tt) * 64;
+        PK_TICK(6)
+        mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
+        PK_TICK(0)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + pass * 32, v);
+          tmem_ld_wait();
+          PK_TICK(2)
+          if (pass == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l + 8 * buf);
+          }
+          if (tt < p.t) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float* d4 = dst + pass * 32 + 4 * c;
+              if (p.skip_init) {
+                *reinterpret_cast<float4*>(d4) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                             "f"(v[4 * c + 2]), "f"(v[4 * c + 3]) : "memory");
+              }
+            }
+          }
+          PK_TICK(5)
+        }
+        PK_TICK(1)
+        have = ti.next(b, m0);
+      }
+    } else {
+      const float kSqrtHalf = 0.70710678118654752440f;
+      for (int i = 0; have; ++i) {
+        const int buf = i & 1;
+        const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
+        const int trow = m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
+        const long long row_off = (static_cast<long long>(b) * p.t + trow) * 64;
+        const bool live = trow < len;
+        PK_TICK(6)
+        mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
+        PK_TICK(0)
+        tcgen05_fence_after();
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + 64 + pass * 32, v);
+          tmem_ld_wait();
+          PK_TICK(2)
+          if (pass == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l + 8 * buf);
+          }
+          uint32_t oh[16], ol[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float y0 = live ? (v[2 * e] + p.out_b[pass * 32 + 2 * e]) * kSqrtHalf : 0.f;
+            const float y1 = live ? (v[2 * e + 1] + p.out_b[pass * 32 + 2 * e + 1]) * kSqrtHalf : 0.f;
+            split2(y0, y1, oh[e], ol[e]);
+          }
+          if (trow < p.t) {
+            st_global_v8(p.y_hi + row_off + pass * 32, oh);
+            st_global_v8(p.y_hi + row_off + pass * 32 + 16, oh + 8);
+            st_global_v8(p.y_lo + row_off + pass * 32, ol);
+            st_global_v8(p.y_lo + row_off + pass * 32 + 16, ol + 8);
+          }
+          PK_TICK(5)
+        }
+        PK_TICK(1)
+        have = ti.next(b, m0);
+      }
+    }
+    PK_TICK(6)
+    if (lane == 0 && quarter == 0 && leader) { PK_TICK_FLUSH(40 + half * 8, 7) }
+  }
+  tcgen05_fence_before();
+  cluster_sync();                      // neither CTA may free its TMEM / exit while the pair's MMAs can still touch it
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+
+}  // namespace fc
+}  // namespace pk
+
+extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream_t stream) {
+  using namespace pk;
+  using namespace pk::fc;
+  PK_CHECK_ARG(a != nullptr, "args is NULL");
+  PK_CHECK_ARG(a->batch > 0 && a->t > 0 && a->dilation >= 1 && a->hop >= 128, "bad batch/t/dilation/hop (hop must be >= 128)");
+  PK_CHECK_ARG(a->x_hi && a->x_lo && a->y_hi && a->y_lo && a->u_hi && a->u_lo && a->p_hi && a->p_lo && a->w1_hi && a->w1_lo &&
+               a->w2_hi && a->w2_lo && a->bias1 && a->bias2 && a->skip, "NULL pointer in pk_pwg_layer_fc_args");
+  PK_CHECK_ARG(a->x_hi != a->y_hi, "layer output must not alias its input");
+  PK_CHECK_ARG(a->u_batches == 1 || a->u_batches == a->batch, "u_batches must be 1 or batch");
+  PK_CHECK_ARG(a->p_rows > 0 && a->p_row0 >= 0 && a->p_row0 + 128 <= a->p_rows && (a->p_ld % 8) == 0 && a->p_frames > 0 &&
+               a->p_frames <= a->p_ld, "bad P plane geometry");
+  PK_CHECK_ARG(sm_count() >= 2, "needs at least one SM pair");
+  CUtensorMap tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
+  int rc;
+  const uint64_t T = a->t, B = a->batch;
+  if ((rc = encode_tmap_bf16_3d(&tx_hi, a->x_hi, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tx_lo, a->x_lo, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
+  // band table planes (u_batches, T, 64): the K window sits in columns 0..15
+  if ((rc = encode_tmap_bf16_3d(&tu_hi, a->u_hi, 64, T, a->u_batches, 64, T * 64, 128))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tu_lo, a->u_lo, 64, T, a->u_batches, 64, T * 64, 128))) return rc;
+  // P planes (batch, p_rows, p_ld): frames are the K axis; columns >= p_frames (and < 0) read as zero
+  const uint64_t prow = a->p_rows, pld = a->p_ld;
+  if ((rc = encode_tmap_bf16_3d(&tp_hi, a->p_hi, a->p_frames, prow, B, pld, prow * pld, 64))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tp_lo, a->p_lo, a->p_frames, prow, B, pld, prow * pld, 64))) return rc;
+  const uint64_t k1 = 5 * kChunkK;     // row pitch of the packed W1 (pk_pwg_residual_layer layout); only the 3 tap chunks are read
+  if ((rc = encode_tmap_bf16_3d(&tw1_hi, a->w1_hi, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw1_lo, a->w1_lo, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw2_hi, a->w2_hi, 64, 128, 1, 64, 0, 64))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tw2_lo, a->w2_lo, 64, 128, 1, 64, 0, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    attr_set = true;
+  }
+  FcLayerArgs p;
+  p.batch = a->batch; p.t = a->t; p.dil = a->dilation; p.hop = a->hop;
+  p.u_bmul = a->u_batches == 1 ? 0 : 1;
+  p.p_row0 = a->p_row0;
+  p.lens = a->lens; p.skip = a->skip; p.skip_init = a->skip_init;
+  constexpr float kLog2e = 1.4426950408889634f;
+  p.k_a = -2.f * kLog2e; p.k_g = -kLog2e;
+  for (int i = 0; i < 64; ++i) {
+    p.gate_c[i] = -2.f * kLog2e * a->bias1[i];
+    p.gate_c[64 + i] = -kLog2e * a->bias1[64 + i];
+    p.out_b[i] = a->bias2[64 + i];
+  }
+  p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
+  p.prof = static_cast<unsigned long long*>(a->prof);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pair_tiles = ((a->t + 255) / 256) * a->batch;
+  const int grid = 2 * std::min(pair_tiles, sm_count() / 2);
+  if (p.prof != nullptr)
+    pwg_layer_fc_kernel<true><<<grid, kPwgThreads, kFcSmem, st>>>(tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
+  else
+    pwg_layer_fc_kernel<false><<<grid, kPwgThreads, kFcSmem, st>>>(tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}

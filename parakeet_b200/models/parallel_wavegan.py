@@ -10,12 +10,13 @@ All arithmetic runs in libparakeet_b200.so (pk_pwg_* in include/parakeet_b200.h)
 """
 import ctypes as C
 import math
+import os
 from typing import Any, Dict, List, Optional
 
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, ops
 from ..layer import Layer
 from ..ops import Split, _ptr, _stream
 
@@ -229,6 +230,8 @@ class PWGGenerator(Layer):
             ws["xb"].hi.zero_()
             ws["xb"].lo.zero_()
         src, dst = ws["xa"], ws["xb"]
+        if os.environ.get("PK_PWG_FRAME_COND", "0") == "1":
+            return self._forward_frame_cond(pk, ws, src, dst, B, T, frames, lens, frame_lens, st)
         args = PwgLayerArgs()
         args.batch, args.t, args.aux_channels = B, T, self.aux_channels
         args.lens = lens.data_ptr() if lens is not None else None
@@ -255,6 +258,75 @@ class PWGGenerator(Layer):
         _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
         self._last_x = src  # layer-30 residual stream (tests)
+        return out
+
+    def _forward_frame_cond(self, pk, ws, src, dst, B, T, frames, lens, frame_lens, st):
+        """EXPERIMENTAL residual stack with frame-rate conditioning (csrc/pwg_fc.cu): conv1x1_aux is applied to
+        conv_in(mel) at frame rate (P), and each layer multiplies the tile-relative band table of the upsampling operator
+        with the 16-frame window of P it touches.  Not validated on a GPU yet - never the default."""
+        from . import _pwg_frame_cond as fc
+        L = _lib.lib()
+        hop, A, NL = self.upsample_factor, self.aux_channels, self.layers
+        if "aux_all" not in pk:
+            # the 30 aux weights stacked as the row operand of one GEMM per forward, P[b] = W_aux_all (30*128 x aux) . m'[b]^T,
+            # and the FIRs of the upsampling stages for the band tables (packed lazily: the default path never needs them)
+            fp = {k: v.detach().float().cpu() for k, v in self._folded().items()}
+            aux_all = torch.cat([fp[f"conv_layers.{i}.conv1x1_aux.weight"][:, :, 0] for i in range(NL)], dim=0)
+            pk["aux_all"] = Split.from_f32(aux_all.contiguous().to(self.device).unsqueeze(0))      # (1, 30*128, aux)
+            firs, off = [], 0
+            for s_ in self.upsample_scales:
+                firs.append(torch.from_numpy(pk["fir_host"][off:off + 2 * s_ + 1].copy()))
+                off += 2 * s_ + 1
+            pk["firs"] = firs
+        m1 = ws["conv_in"]                                               # (B, frames, aux) written by pk_pwg_upsample above
+        if frame_lens is not None:
+            ops.mask_rows_(m1, frame_lens)                               # frames past an utterance's end contribute nothing
+        m1s = Split.from_f32(m1)
+        Fp = (frames + 7) // 8 * 8
+        P = Split.zeros((B, NL * 128, Fp), self.device)
+        a_spec = dict(rows=NL * 128, cols=A, ld=A, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
+        b_spec = dict(rows=frames, cols=A, ld=A, batch_stride=frames * A, batches=B, bmul=1, hmul=0, col0=0, colh=0)
+        ops.batched_matmul_nt(pk["aux_all"], m1s, batch=B, heads=1, m=NL * 128, n=frames, k=A, a_spec=a_spec, b_spec=b_spec,
+                              y_split=P, y_batch_stride=NL * 128 * Fp, y_head_stride=0, y_ld=Fp)
+        # band tables: one per distinct utterance length (constants of the model), shared when the batch is not ragged
+        cache = self.__dict__.setdefault("_band_tables", {})
+
+        def table(nf):
+            if nf not in cache:
+                tb = torch.zeros(nf * hop, 64, dtype=torch.float32)
+                tb[:, :fc.KWIN] = fc.tile_band_table(pk["firs"], self.upsample_scales, nf).float()
+                cache[nf] = tb
+            return cache[nf]
+        if frame_lens is None:
+            U = Split.from_f32(table(frames).to(self.device).unsqueeze(0))
+            u_batches = 1
+        else:
+            full = torch.zeros(B, T, 64, dtype=torch.float32)
+            for i, nf in enumerate(frame_lens.cpu().tolist()):
+                if nf > 0:
+                    full[i, :nf * hop] = table(int(nf))
+            U = Split.from_f32(full.to(self.device))
+            u_batches = B
+        args = _lib.PwgLayerFcArgs()
+        args.batch, args.t, args.hop = B, T, hop
+        args.lens = lens.data_ptr() if lens is not None else None
+        args.u_hi, args.u_lo, args.u_batches = U.hi.data_ptr(), U.lo.data_ptr(), u_batches
+        args.p_hi, args.p_lo, args.p_rows, args.p_ld, args.p_frames = P.hi.data_ptr(), P.lo.data_ptr(), NL * 128, Fp, frames
+        args.skip = ws["skip"].data_ptr()
+        args.prof = self._prof.data_ptr() if getattr(self, "_prof", None) is not None else None
+        for i, lay in enumerate(pk["layers"]):
+            args.dilation, args.p_row0 = lay["dil"], i * 128
+            args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
+            args.w1_hi, args.w1_lo = lay["w1"].hi.data_ptr(), lay["w1"].lo.data_ptr()
+            args.w2_hi, args.w2_lo = lay["w2"].hi.data_ptr(), lay["w2"].lo.data_ptr()
+            args.bias1, args.bias2 = lay["b1"].ctypes.data, lay["b2"].ctypes.data
+            args.skip_init = 1 if i == 0 else 0
+            _lib.check(L.pk_pwg_residual_layer_fc(C.byref(args), st), "pk_pwg_residual_layer_fc")
+            src, dst = dst, src
+        out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
+        _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
+                                 _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
+        self._last_x = src
         return out
 
     def upsample(self, c):

@@ -107,7 +107,7 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
         pytest.skip("no C compiler")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     mirrors = {"pk_operand": _lib.Operand, "pk_conv_gemm_args": _lib.ConvGemmArgs, "pk_pwg_layer_args": _lib.PwgLayerArgs,
-               "pk_gemm_epilogue": _lib.GemmEpilogue}
+               "pk_gemm_epilogue": _lib.GemmEpilogue, "pk_pwg_layer_fc_args": _lib.PwgLayerFcArgs}
     lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "parakeet_b200.h"', "int main(void) {"]
     for cname, cls in mirrors.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
