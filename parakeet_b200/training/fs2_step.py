@@ -14,6 +14,7 @@ torch is used for buffers, views, permutes / copies (layout plumbing) and torch.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -21,6 +22,7 @@ import torch.distributed as dist
 from .. import _lib, ops
 from ..models.fastspeech2 import FastSpeech2, _i32
 from ..ops import Split, _ptr, _stream
+from ..graph import GraphRunner
 from .flat import FlatBuffers
 
 BUFFERS = ("_mean", "_variance")
@@ -60,6 +62,10 @@ class FastSpeech2TrainStep:
         self.adam_v = torch.zeros(self.buffers.total, dtype=torch.float32, device=dev)
         model._packed = None
         self.step_count = 0
+        # EXPERIMENTAL (PK_TRAIN_GRAPH=1, default off, not validated on a GPU yet): forward + backward replayed as a CUDA graph per
+        # batch shape (B, Tmax, Lmax) once a shape repeats (bucketed samplers); the step is host-bound (~600 launches).
+        self._fb_graphs = GraphRunner(max_graphs=16)
+        self.use_graphs = os.environ.get("PK_TRAIN_GRAPH", "0") == "1"
         self.sums = torch.zeros(4096, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -387,9 +393,18 @@ class FastSpeech2TrainStep:
                                      _ptr(self.grads["encoder.embed.1.alpha"]), st), "pk_embed_pe_bwd")
         return losses
 
+    def _forward_backward_graphed(self, batch):
+        dev = self.m.device
+        order = ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")
+        dtypes = (torch.int64, torch.int64, torch.float32, torch.int64, torch.int64, torch.float32, torch.float32)
+        tensors = [batch[k].to(dev, dt).contiguous() for k, dt in zip(order, dtypes)]
+        key = tuple(tuple(t.shape) for t in tensors)
+        fn = lambda *ts: self.forward_backward(dict(zip(order, ts)))
+        return self._fb_graphs.run(key, fn, tensors).clone()
+
     def step(self, batch):
         """One update: returns the four loss values (device tensor: l1, duration, pitch, energy)."""
-        losses = self.forward_backward(batch)
+        losses = self._forward_backward_graphed(batch) if self.use_graphs else self.forward_backward(batch)
         if self.world > 1:
             self.buffers.all_reduce_grads(self.group)                                # the one exchange step of the path
         self.step_count += 1
