@@ -265,7 +265,7 @@ def main():
                    "api": "PWGGenerator.forward(x, c) with pinned host tensors"},
            "roofline": roofline}
 
-    if not args.no_extra:
+    if not args.no_extra and world == 1:      # single-GPU side metrics; the scaling runs report the headline only
         # FastSpeech2 (cfg3's acoustic half) and the FS2 -> PWG pipeline, reported alongside the headline
         try:
             import math
