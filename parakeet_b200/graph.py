@@ -26,11 +26,12 @@ class GraphRunner:
         self.enabled = os.environ.get("PK_CUDA_GRAPHS", "1") != "0"
         self.max_graphs = max_graphs
         self._seen = set()
+        self._disabled = set()
         self._graphs = {}
         self.replays = 0
 
     def run(self, key, fn, inputs):
-        if not self.enabled:
+        if not self.enabled or key in self._disabled:
             return fn(*inputs)
         ent = self._graphs.get(key)
         if ent is None:
@@ -40,8 +41,13 @@ class GraphRunner:
             static_in = [t.clone() for t in inputs]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = fn(*static_in)
+            try:
+                with torch.cuda.graph(graph):
+                    out = fn(*static_in)
+            except Exception:                      # capture refused (another thread touched CUDA, unsupported call, ...):
+                torch.cuda.synchronize()           # never let the graph layer break the call - run this key eagerly from now on
+                self._disabled.add(key)
+                return fn(*inputs)
             ent = (graph, static_in, out)
             self._graphs[key] = ent
         graph, static_in, out = ent
@@ -54,3 +60,4 @@ class GraphRunner:
     def clear(self):
         self._graphs.clear()
         self._seen.clear()
+        self._disabled.clear()
