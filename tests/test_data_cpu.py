@@ -72,3 +72,15 @@ def test_distributed_batch_sampler_contract():
     assert list(a) != list(b)                                         # reshuffled per epoch
     c = data.DistributedBatchSampler(10, 4, 1, 0, shuffle=False, drop_last=False)
     assert list(c) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]] and len(c) == 3
+
+
+def test_batch_sequences_against_vectors_produced_by_the_reference_code():
+    """tests/golden/ref_batch_sequences.npz was written by scripts/make_golden_ref.py, which EXECUTES the reference's own
+    parakeet/data/batch.py:170-189 (numpy only) - the one piece of the path whose reference implementation can run here."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_batch_sequences.npz"))
+    n = int(g["n"])
+    for name in ("text", "speech", "pitch"):
+        seqs = [g[f"{name}_in{i}"] for i in range(n)]
+        got = data.batch_sequences(seqs)
+        assert got.dtype == g[f"{name}_out"].dtype and np.array_equal(got, g[f"{name}_out"]), name
