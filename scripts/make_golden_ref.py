@@ -1,40 +1,165 @@
-"""Golden vectors produced by RUNNING the reference's own code - the few functions on the path that need numpy only
-(everything else imports paddle, which cannot be installed here).  Loaded by file path so that `parakeet/__init__.py` (which
-imports paddle) is never executed.  Run in the build container (needs /root/reference); the .npz travels with the repo.
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN PYTHON for the hot path.
 
-    python scripts/make_golden_ref.py
+PaddlePaddle cannot be installed in the build container, so the reference cannot run as is.  Its model code is plain Python
+that calls ~60 Paddle primitives; `scripts/refexec/paddle_standin.py` maps those primitives onto torch (same mathematical
+definitions; the few Paddle-specific semantics are the ones oracle/README.md lists), `scripts/refexec/loader.py` imports the
+reference's files from /root/reference without running `parakeet/__init__.py`.  Under that stand-in this script builds the
+reference's own FastSpeech2 / PWGGenerator / ConditionalWaveFlow classes, loads the oracle's seeded Paddle-layout state dicts
+into them (which also checks every state-dict key and shape against the reference's class tree) and records what the
+REFERENCE code computes.  tests/test_oracle_cpu.py then holds the oracle to these vectors.
+
+    python scripts/make_golden_ref.py        # needs /root/reference; writes tests/golden/ref_executed*.npz
 """
 import importlib.util
 import os
+import sys
 
 import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+from refexec import loader, paddle_standin  # noqa: E402
 
 REF = "/root/reference/parakeet"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_batch_sequences.npz")
+GOLD = os.path.join(ROOT, "tests", "golden")
+T = paddle_standin.T
 
 
-def load(path, name):
+def load_by_path(path, name):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
 
 
-def main():
-    batch = load(os.path.join(REF, "data", "batch.py"), "ref_batch")
+def small_pieces(out):
+    # numpy-only collate padding (parakeet/data/batch.py:170-189)
+    batch = load_by_path(os.path.join(REF, "data", "batch.py"), "ref_batch")
     rng = np.random.RandomState(20260923)
-    out = {}
     lengths = [5, 11, 3, 8]
-    text = [rng.randint(1, 70, size=n).astype(np.int64) for n in lengths]
-    speech = [rng.randn(3 * n, 7).astype(np.float32) for n in lengths]
-    pitch = [rng.randn(n, 1).astype(np.float32) for n in lengths]
-    for name, seqs in (("text", text), ("speech", speech), ("pitch", pitch)):
-        for i, s in enumerate(seqs):
+    seqs = {"text": [rng.randint(1, 70, size=n).astype(np.int64) for n in lengths],
+            "speech": [rng.randn(3 * n, 7).astype(np.float32) for n in lengths],
+            "pitch": [rng.randn(n, 1).astype(np.float32) for n in lengths]}
+    for name, ss in seqs.items():
+        for i, s in enumerate(ss):
             out[f"{name}_in{i}"] = s
-        out[f"{name}_out"] = batch.batch_sequences(seqs)              # parakeet/data/batch.py:170-189, executed
+        out[f"{name}_out"] = batch.batch_sequences(ss)
     out["n"] = np.asarray(len(lengths))
-    np.savez(OUT, **out)
-    print("wrote", OUT, {k: v.shape for k, v in out.items() if k.endswith("_out")})
+    # padding masks (modules/nets_utils.py:54-125) and the length regulator (fastspeech2_predictor/length_regulator.py:46-89)
+    from parakeet.modules import nets_utils as nets
+    from parakeet.modules.fastspeech2_predictor.length_regulator import LengthRegulator
+    for i, lens in enumerate(([5, 3, 2], [1], [7, 7, 4, 9])):
+        out[f"mask_len{i}"] = np.asarray(lens, dtype=np.int64)
+        out[f"mask_pad{i}"] = nets.make_pad_mask(T(torch.tensor(lens))).numpy()
+        out[f"mask_nonpad{i}"] = nets.make_non_pad_mask(lens).numpy()
+    lr = LengthRegulator()
+    rng = np.random.RandomState(7)
+    cases = {"a": ([[1, 2, 2, 1], [3, 1, 4, 0]], 3),                                  # tests/unit/test_expansion.py:20-24
+             "b": (rng.randint(0, 6, size=(3, 17)).tolist(), 8), "c": ([[0, 0, 5], [2, 0, 0]], 4)}
+    for name, (ds, c) in cases.items():
+        d = np.asarray(ds, dtype=np.int64)
+        x = rng.randn(d.shape[0], d.shape[1], c).astype(np.float32)
+        y = lr(T(torch.from_numpy(x)), T(torch.from_numpy(d)))
+        out[f"lr_{name}_x"], out[f"lr_{name}_d"], out[f"lr_{name}_y"] = x, d, y.numpy()
+
+
+def check_keys(ref, params, what):
+    own = dict(ref.named_parameters())
+    own.update(dict(ref.named_buffers()))
+    own = {k: v for k, v in own.items() if "generated_tensor_" not in k}
+    missing, extra = [k for k in own if k not in params], [k for k in params if k not in own]
+    bad = [k for k in own if k in params and tuple(own[k].shape) != tuple(params[k].shape)]
+    assert not missing and not extra and not bad, (what, missing[:5], extra[:5], bad[:5])
+    return sorted(own)
+
+
+def fastspeech2(out):
+    from oracle import fastspeech2 as ofs
+    from parakeet.models.fastspeech2.fastspeech2 import FastSpeech2, FastSpeech2Loss
+    cfg = dict(ofs.LJSPEECH_MODEL_CFG)
+    ref = FastSpeech2(idim=80, odim=80, **cfg)
+    ref.eval()
+    params = ofs.synth_params(1)
+    out["fs2_keys"] = np.asarray(check_keys(ref, params, "FastSpeech2"))
+    ref.set_state_dict(params)
+    with torch.no_grad():
+        xs, _ = ofs.synth_text(1, [100])                                               # cfg1
+        out["fs2_inf_text"] = xs[0].numpy()
+        out["fs2_inf_mel"] = ref.inference(T(xs[0])).numpy()
+        out["fs2_inf_mel_alpha"] = ref.inference(T(xs[0]), alpha=1.3).numpy()        # uses the stand-in's round (restated)
+        b = ofs.synth_train_batch(5, [23, 31, 17])
+        for k, v in b.items():
+            out[f"fs2_fwd_{k}"] = v.numpy()
+        before, after, d_outs, p_outs, e_outs, ys, olens = ref(T(b["text"]), T(b["text_lengths"]), T(b["speech"]), T(b["speech_lengths"]),
+                                                               T(b["durations"]), T(b["pitch"]), T(b["energy"]))
+        for k, v in (("before", before), ("after", after), ("d_outs", d_outs), ("p_outs", p_outs), ("e_outs", e_outs)):
+            out[f"fs2_fwd_out_{k}"] = v.numpy()
+        crit = FastSpeech2Loss(use_masking=True, use_weighted_masking=False)
+        l1, dur, pitch, energy = crit(after_outs=after, before_outs=before, d_outs=d_outs, p_outs=p_outs, e_outs=e_outs, ys=ys,
+                                      ds=T(b["durations"]), ps=T(b["pitch"]), es=T(b["energy"]), ilens=T(b["text_lengths"]), olens=olens)
+        out["fs2_loss"] = np.asarray([float(l1), float(dur), float(pitch), float(energy)], dtype=np.float64)
+
+
+def parallel_wavegan(out):
+    from oracle import pwg as opwg
+    from parakeet.models.parallel_wavegan.parallel_wavegan import PWGGenerator
+    cfg = dict(opwg.DEFAULT_GENERATOR_PARAMS)
+    cfg["use_weight_norm"] = False                                                    # the folded weights are loaded
+    ref = PWGGenerator(**cfg)
+    ref.eval()
+    folded = opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True))
+    out["pwg_keys"] = np.asarray(check_keys(ref, folded, "PWGGenerator"))
+    ref.set_state_dict(folded)
+    x, c = opwg.synth_inputs(2, batch=2, mel_frames=10)
+    with torch.no_grad():
+        out["pwg_x"], out["pwg_c"] = x.numpy(), c.numpy()
+        out["pwg_y"] = ref(T(x), T(c)).numpy()
+    # with weight norm applied by the reference's own apply_weight_norm: the g / v parametrisation and its 1-D weight_g
+    cfg["use_weight_norm"] = True
+    ref2 = PWGGenerator(**cfg)
+    ref2.eval()
+    wn = opwg.synth_params(2, weight_norm=True)
+    out["pwg_wn_keys"] = np.asarray(check_keys(ref2, wn, "PWGGenerator(weight_norm)"))
+    ref2.set_state_dict(wn)
+    with torch.no_grad():
+        out["pwg_y_weight_norm"] = ref2(T(x), T(c)).numpy()
+
+
+def waveflow(out):
+    from oracle import waveflow as owf
+    from parakeet.models.waveflow import ConditionalWaveFlow
+    ref = ConditionalWaveFlow(upsample_factors=[16, 16], n_flows=8, n_layers=8, n_group=16, channels=64, n_mels=80, kernel_size=[3, 3])
+    ref.eval()
+    params = owf.synth_params(4)
+    out["wf_keys"] = np.asarray(check_keys(ref, params, "ConditionalWaveFlow"))
+    ref.set_state_dict(params)
+    g = torch.Generator().manual_seed(4)
+    mel = torch.randn(2, 80, 9, generator=g) * 0.5 - 3
+    with torch.no_grad():
+        cond = ref.encoder(T(mel), trim_conv_artifact=True)
+        z = torch.randn(2, cond.shape[-1], generator=g)
+        out["wf_mel"], out["wf_z"] = mel.numpy(), z.numpy()
+        out["wf_cond"] = cond.numpy()
+        out["wf_x"] = ref.decoder.inverse(T(z), cond).numpy()
+
+
+def main():
+    uninstall = loader.install(paddle_standin.build())
+    try:
+        small, models = {}, {}
+        small_pieces(small)
+        fastspeech2(models)
+        parallel_wavegan(models)
+        waveflow(models)
+    finally:
+        uninstall()
+    np.savez(os.path.join(GOLD, "ref_executed.npz"), **small)
+    np.savez_compressed(os.path.join(GOLD, "ref_executed_models.npz"), **models)
+    for name, d in (("ref_executed.npz", small), ("ref_executed_models.npz", models)):
+        print(name, os.path.getsize(os.path.join(GOLD, name)) // 1024, "KB", len(d), "arrays")
 
 
 if __name__ == "__main__":

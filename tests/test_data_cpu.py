@@ -75,10 +75,10 @@ def test_distributed_batch_sampler_contract():
 
 
 def test_batch_sequences_against_vectors_produced_by_the_reference_code():
-    """tests/golden/ref_batch_sequences.npz was written by scripts/make_golden_ref.py, which EXECUTES the reference's own
-    parakeet/data/batch.py:170-189 (numpy only) - the one piece of the path whose reference implementation can run here."""
+    """tests/golden/ref_executed.npz was written by scripts/make_golden_ref.py, which EXECUTES the reference's own
+    parakeet/data/batch.py:170-189 (numpy only)."""
     import os
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_batch_sequences.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_executed.npz"))
     n = int(g["n"])
     for name in ("text", "speech", "pitch"):
         seqs = [g[f"{name}_in{i}"] for i in range(n)]

@@ -286,3 +286,33 @@ def test_pwg_frame_rate_conditioning_tables_reproduce_the_aux_path():
             got = table[t0:t0 + fc.TILE] @ win
             worst = max(worst, float((got - ref[t0:t0 + fc.TILE]).abs().max()))
         assert worst < 1e-12 * max(1.0, float(ref.abs().max())), (frames, worst)
+
+
+def test_length_regulator_against_vectors_produced_by_the_reference_code():
+    """tests/golden/ref_executed.npz: outputs of the reference's own LengthRegulator.forward (its numpy expansion-matrix loop,
+    length_regulator.py:46-89) executed by scripts/make_golden_ref.py behind a ten-line torch stand-in for the four paddle
+    names it touches.  The oracle (and through tests/test_gpu_kernels.py the CUDA kernel) must reproduce them bit for bit,
+    including zero durations and the zero rows past each utterance's total."""
+    import os
+    from oracle import fastspeech2 as ofs
+    g = np.load(os.path.join(GOLD, "ref_executed.npz"))
+    for name in ("a", "b", "c"):
+        x, d, y = (torch.from_numpy(g[f"lr_{name}_{k}"]) for k in ("x", "d", "y"))
+        got = ofs.length_regulator(x, d)
+        assert tuple(got.shape) == tuple(y.shape) and torch.equal(got, y), name
+        # rows past an utterance's own total are exactly zero, rows before it are exact copies
+        tot = d.sum(1)
+        for b in range(d.shape[0]):
+            assert y[b, int(tot[b]):].abs().sum() == 0
+    assert list(g["lr_a_y"].shape) == [2, 8, 3]                      # tests/unit/test_expansion.py:24
+
+
+def test_pad_masks_against_vectors_produced_by_the_reference_code():
+    """make_pad_mask / make_non_pad_mask (modules/nets_utils.py:54-125) executed by scripts/make_golden_ref.py."""
+    import os
+    from oracle import fastspeech2 as ofs
+    g = np.load(os.path.join(GOLD, "ref_executed.npz"))
+    for i in range(3):
+        lens = torch.from_numpy(g[f"mask_len{i}"])
+        assert np.array_equal(ofs.make_pad_mask(lens).numpy(), g[f"mask_pad{i}"])
+        assert np.array_equal(ofs.make_non_pad_mask(lens).numpy(), g[f"mask_nonpad{i}"])

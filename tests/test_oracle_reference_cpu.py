@@ -1,0 +1,83 @@
+"""The oracle held to outputs of the REFERENCE'S OWN CODE.
+
+tests/golden/ref_executed_models.npz is written by scripts/make_golden_ref.py, which imports the reference's model files from
+/root/reference and runs them - FastSpeech2.inference / forward / FastSpeech2Loss, PWGGenerator.forward (plain and through the
+reference's own apply_weight_norm), ConditionalWaveFlow encoder + WaveFlow.inverse - on a torch-backed stand-in for the Paddle
+primitives they call (scripts/refexec/paddle_standin.py), with the oracle's seeded Paddle-layout state dicts loaded into the
+reference classes.  That run also asserts that every state-dict key and shape of the reference's class tree equals ours.
+The vectors travel with the repo; these tests need neither /root/reference nor a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-6        # same arithmetic, same torch kernels underneath: the oracle reproduces the executed reference to rounding
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLD, "ref_executed_models.npz"))
+
+
+def test_state_dict_keys_equal_the_reference_class_trees(g):
+    from oracle import fastspeech2 as ofs
+    from oracle import pwg as opwg
+    from oracle import waveflow as owf
+    assert sorted(ofs.synth_params(1)) == list(g["fs2_keys"])
+    assert sorted(opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True))) == list(g["pwg_keys"])
+    assert sorted(opwg.synth_params(2, weight_norm=True)) == list(g["pwg_wn_keys"])
+    assert sorted(owf.synth_params(4)) == list(g["wf_keys"])
+    # and the CUDA-side host classes expose exactly the same names (the checkpoint boundary of SURVEY 8b)
+    from parakeet_b200.models import ConditionalWaveFlow, FastSpeech2, PWGGenerator
+    fs = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, device="cpu")
+    assert sorted(fs.state_dict()) == list(g["fs2_keys"])
+    gen = PWGGenerator(**opwg.DEFAULT_GENERATOR_PARAMS, device="cpu")
+    assert sorted(gen.state_dict()) == list(g["pwg_wn_keys"])
+    wf = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device="cpu")
+    assert sorted(wf.state_dict()) == list(g["wf_keys"])
+
+
+def test_fastspeech2_oracle_equals_executed_reference(g):
+    from oracle import fastspeech2 as ofs
+    params = ofs.synth_params(1)
+    text = torch.from_numpy(g["fs2_inf_text"])
+    with torch.no_grad():
+        mel = ofs.fs2_inference(params, None, text)
+        mel13 = ofs.fs2_inference(params, None, text, alpha=1.3)
+    assert tuple(mel.shape) == g["fs2_inf_mel"].shape and rel_err(mel, torch.from_numpy(g["fs2_inf_mel"])) < TOL
+    assert tuple(mel13.shape) == g["fs2_inf_mel_alpha"].shape and rel_err(mel13, torch.from_numpy(g["fs2_inf_mel_alpha"])) < TOL
+    b = {k: torch.from_numpy(g[f"fs2_fwd_{k}"]) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+    with torch.no_grad():
+        out = ofs.fs2_forward(params, None, b["text"], b["text_lengths"], b["speech_lengths"], b["durations"], b["pitch"], b["energy"])
+    for name, t in zip(("before", "after", "d_outs", "p_outs", "e_outs"), out[:5]):
+        ref = torch.from_numpy(g[f"fs2_fwd_out_{name}"])
+        assert tuple(t.shape) == tuple(ref.shape) and rel_err(t, ref) < TOL, name
+    before, after, d_outs, p_outs, e_outs = out[:5]
+    losses = ofs.fs2_loss(after, before, d_outs, p_outs, e_outs, b["speech"], b["durations"], b["pitch"], b["energy"], b["text_lengths"],
+                          b["speech_lengths"])
+    assert np.allclose([float(v) for v in losses[:4]], g["fs2_loss"], rtol=1e-5)       # l1, duration, pitch, energy
+
+
+def test_pwg_oracle_equals_executed_reference(g):
+    from oracle import pwg as opwg
+    wn = opwg.synth_params(2, weight_norm=True)
+    x, c = torch.from_numpy(g["pwg_x"]), torch.from_numpy(g["pwg_c"])
+    with torch.no_grad():
+        y = opwg.generator_forward(opwg.fold_weight_norm(wn), x, c)
+    assert rel_err(y, torch.from_numpy(g["pwg_y"])) < TOL
+    assert rel_err(y, torch.from_numpy(g["pwg_y_weight_norm"])) < 1e-5               # the reference's own weight_norm(g, v) path
+
+
+def test_waveflow_oracle_equals_executed_reference(g):
+    from oracle import waveflow as owf
+    folded = owf.fold_weight_norm(owf.synth_params(4))
+    mel, z = torch.from_numpy(g["wf_mel"]), torch.from_numpy(g["wf_z"])
+    with torch.no_grad():
+        cond = owf.encoder(folded, mel, 2)
+        x = owf.infer(folded, mel, z)
+    assert rel_err(cond, torch.from_numpy(g["wf_cond"])) < 1e-5
+    assert tuple(x.shape) == g["wf_x"].shape and rel_err(x, torch.from_numpy(g["wf_x"])) < 1e-5
