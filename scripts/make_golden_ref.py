@@ -146,6 +146,58 @@ def waveflow(out):
         out["wf_x"] = ref.decoder.inverse(T(z), cond).numpy()
 
 
+def wrappers_and_stft(out):
+    """FastSpeech2Inference / PWGInference (normaliser wrappers, PWG's replicate padding and transposes) and modules/audio.STFT."""
+    import paddle
+    from oracle import fastspeech2 as ofs
+    from oracle import pwg as opwg
+    from parakeet.models.fastspeech2.fastspeech2 import FastSpeech2, FastSpeech2Inference
+    from parakeet.models.parallel_wavegan.parallel_wavegan import PWGGenerator, PWGInference
+    from parakeet.modules.audio import STFT
+    from parakeet.modules.normalizer import ZScore
+    g = torch.Generator().manual_seed(11)
+    mu, sigma = torch.randn(80, generator=g), torch.rand(80, generator=g) + 0.5
+    out["wr_mu"], out["wr_sigma"] = mu.numpy(), sigma.numpy()
+    fs = FastSpeech2(idim=80, odim=80, **ofs.LJSPEECH_MODEL_CFG)
+    fs.eval()
+    fs.set_state_dict(ofs.synth_params(1))
+    text = torch.randint(1, 79, (20,), generator=g)
+    with torch.no_grad():
+        logmel = FastSpeech2Inference(ZScore(T(mu), T(sigma)), fs)(T(text))
+    out["wr_text"], out["wr_logmel"] = text.numpy(), logmel.numpy()
+    cfg = dict(opwg.DEFAULT_GENERATOR_PARAMS)
+    cfg["use_weight_norm"] = False
+    gen = PWGGenerator(**cfg)
+    gen.eval()
+    gen.set_state_dict(opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True)))
+    mel = torch.randn(6, 80, generator=g)
+    noise = torch.randn(1, 1, 6 * 300, generator=g)
+    real_randn = paddle.randn
+    paddle.randn = lambda shape, dtype=None: T(noise)                 # inference() draws its own noise: supply ours
+    try:
+        with torch.no_grad():
+            wav = PWGInference(ZScore(T(mu), T(sigma)), gen)(T(mel))
+    finally:
+        paddle.randn = real_randn
+    out["wr_pwg_logmel"], out["wr_pwg_noise"], out["wr_pwg_wav"] = mel.numpy(), noise.numpy(), wav.numpy()
+    wavs = torch.randn(2, 3000, generator=g)
+    out["stft_x"] = wavs.numpy()
+    for tag, (n_fft, hop, win) in (("a", (512, 128, 512)), ("b", (1024, 120, 600))):
+        st = STFT(n_fft, hop, win, window="hann")
+        with torch.no_grad():
+            re, im = st(T(wavs))
+            mag = st.magnitude(T(wavs))
+        out[f"stft_{tag}_re"], out[f"stft_{tag}_im"], out[f"stft_{tag}_mag"] = re.numpy(), im.numpy(), mag.numpy()
+    # MultiResolutionSTFTLoss (modules/stft_loss.py:163-219): paddle.signal.stft mapped to torch.stft; the clipping, the
+    # transposes, the Frobenius ratio, the log-magnitude L1 and the mean over resolutions are the reference's code
+    from parakeet.modules.stft_loss import MultiResolutionSTFTLoss
+    other = torch.randn(2, 3000, generator=g) * 0.3
+    out["mrstft_y"] = other.numpy()
+    with torch.no_grad():
+        sc, mag = MultiResolutionSTFTLoss()(T(wavs), T(other))
+    out["mrstft_loss"] = np.asarray([float(sc), float(mag)], dtype=np.float64)
+
+
 def main():
     uninstall = loader.install(paddle_standin.build())
     try:
@@ -154,6 +206,7 @@ def main():
         fastspeech2(models)
         parallel_wavegan(models)
         waveflow(models)
+        wrappers_and_stft(models)
     finally:
         uninstall()
     np.savez(os.path.join(GOLD, "ref_executed.npz"), **small)

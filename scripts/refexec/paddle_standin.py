@@ -69,6 +69,12 @@ class Tensor(torch.Tensor):
     def place(self):
         return "cpu"
 
+    def real(self):
+        return torch.real(self)
+
+    def imag(self):
+        return torch.imag(self)
+
     @property
     def name(self):                                  # paddle tensors carry auto-generated unique names
         n = getattr(self, "_pk_name", None)
@@ -151,6 +157,19 @@ def build():
     P.unsqueeze = lambda x, axis: T(torch.unsqueeze(x, axis))
     P.squeeze = lambda x, axis=None: T(torch.squeeze(x) if axis is None else torch.squeeze(x, axis))
     P.shape = lambda x: list(x.shape)
+    P.divide = lambda a, b: T(a / b)
+    P.norm = lambda x, p="fro", axis=None, keepdim=False: T(torch.linalg.norm(x.reshape(-1)) if (axis is None and p == "fro") else torch.norm(x, p=p, dim=axis, keepdim=keepdim))
+    sig = types.ModuleType("paddle.signal")
+
+    def p_stft(x, n_fft, hop_length=None, win_length=None, window=None, center=True, pad_mode="reflect", normalized=False, onesided=True):
+        # paddle.signal.stft is a Paddle kernel: mapped to torch.stft of the same definition (window centre-padded to n_fft)
+        w = window.to(x.dtype) if window is not None else None
+        return T(torch.stft(x, n_fft, hop_length, win_length, window=w, center=center, pad_mode=pad_mode, normalized=normalized,
+                            onesided=onesided, return_complex=True))
+    sig.stft = p_stft
+    P.signal = sig
+    P.subtract = lambda a, b: T(a - b)
+    P.get_default_dtype = lambda: "float32"
     P.multiply = lambda a, b: T(a * b)
     P.add = lambda a, b: T(a + b)
 
@@ -403,6 +422,8 @@ def build():
     F.log_softmax = lambda x, axis=-1: T(torch.log_softmax(x, dim=axis))
     F.dropout = lambda x, p=0.5, training=True, **k: x
     F.relu = lambda x: T(torch.relu(x))
+    F.l1_loss = lambda a, b, reduction="mean": T(TF.l1_loss(a, b, reduction=reduction))
+    F.mse_loss = lambda a, b, reduction="mean": T(TF.mse_loss(a, b, reduction=reduction))
     F.leaky_relu = lambda x, negative_slope=0.01: T(TF.leaky_relu(x, negative_slope))
     F.sigmoid = lambda x: T(torch.sigmoid(x))
     F.tanh = lambda x: T(torch.tanh(x))
@@ -450,6 +471,19 @@ def build():
     P.distributed = dist
     P.gather = lambda x, index, axis=0: T(torch.index_select(x, axis, index.reshape(-1).to(torch.int64)))
     P.index_select = lambda x, index, axis=0: T(torch.index_select(x, axis, index.reshape(-1).to(torch.int64)))
+    # librosa is not installed; modules/audio.py imports it at module level.  pad_center (centre zero-padding of the window to
+    # n_fft) is restated; filters.mel is NOT provided - MelScale is checked against torchaudio elsewhere, not executed here.
+    import numpy as _np
+    librosa = types.ModuleType("librosa")
+    librosa.util = types.ModuleType("librosa.util")
+
+    def pad_center(data, size, axis=-1, mode="constant"):
+        n = data.shape[axis]
+        lpad = (size - n) // 2
+        widths = [(0, 0)] * data.ndim
+        widths[axis] = (lpad, size - n - lpad)
+        return _np.pad(data, widths, mode=mode)
+    librosa.util.pad_center = pad_center
     tg = types.ModuleType("typeguard")                 # the installed typeguard rejects the reference's `x: int = None` defaults
     tg.check_argument_types = lambda *a, **k: True
-    return {"typeguard": tg, "paddle": P, "paddle.distributed": dist, "paddle.nn": nn, "paddle.nn.functional": F, "paddle.nn.initializer": init, "paddle.nn.utils": utils}
+    return {"typeguard": tg, "librosa": librosa, "librosa.util": librosa.util, "paddle": P, "paddle.distributed": dist, "paddle.signal": sig, "paddle.nn": nn, "paddle.nn.functional": F, "paddle.nn.initializer": init, "paddle.nn.utils": utils}

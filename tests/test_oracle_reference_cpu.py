@@ -81,3 +81,30 @@ def test_waveflow_oracle_equals_executed_reference(g):
         x = owf.infer(folded, mel, z)
     assert rel_err(cond, torch.from_numpy(g["wf_cond"])) < 1e-5
     assert tuple(x.shape) == g["wf_x"].shape and rel_err(x, torch.from_numpy(g["wf_x"])) < 1e-5
+
+
+def test_inference_wrappers_and_stft_equal_executed_reference(g):
+    """FastSpeech2Inference (inference + ZScore.inverse), PWGInference (ZScore + replicate padding + transposes, the reference's
+    own inference() with the noise supplied) and modules/audio.STFT (DFT-matrix conv, real / imag / magnitude)."""
+    from oracle import fastspeech2 as ofs
+    from oracle import pwg as opwg
+    from oracle import stft as ostft
+    mu, sigma = torch.from_numpy(g["wr_mu"]), torch.from_numpy(g["wr_sigma"])
+    with torch.no_grad():
+        logmel = ofs.fs2_inference_denorm(ofs.synth_params(1), None, torch.from_numpy(g["wr_text"]), mu, sigma)
+    assert tuple(logmel.shape) == g["wr_logmel"].shape and rel_err(logmel, torch.from_numpy(g["wr_logmel"])) < TOL
+    folded = opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True))
+    with torch.no_grad():
+        wav = opwg.pwg_inference(folded, torch.from_numpy(g["wr_pwg_logmel"]), mu, sigma, torch.from_numpy(g["wr_pwg_noise"]))
+    assert tuple(wav.shape) == g["wr_pwg_wav"].shape and rel_err(wav, torch.from_numpy(g["wr_pwg_wav"])) < TOL
+    x = torch.from_numpy(g["stft_x"])
+    for tag, (n_fft, hop, win) in (("a", (512, 128, 512)), ("b", (1024, 120, 600))):
+        re, im = ostft.stft_dft_conv(x, n_fft, hop, win)
+        assert rel_err(re, torch.from_numpy(g[f"stft_{tag}_re"])) < 1e-5 and rel_err(im, torch.from_numpy(g[f"stft_{tag}_im"])) < 1e-5
+        assert rel_err(torch.sqrt(re ** 2 + im ** 2), torch.from_numpy(g[f"stft_{tag}_mag"])) < 1e-5
+
+
+def test_multi_resolution_stft_loss_equals_executed_reference(g):
+    from oracle import stft as ostft
+    sc, mag = ostft.multi_resolution_stft_loss(torch.from_numpy(g["stft_x"]), torch.from_numpy(g["mrstft_y"]))
+    assert np.allclose([float(sc), float(mag)], g["mrstft_loss"], rtol=2e-5)
