@@ -103,6 +103,50 @@ def fastspeech2(out):
         out["fs2_loss"] = np.asarray([float(l1), float(dur), float(pitch), float(energy)], dtype=np.float64)
 
 
+def fastspeech2_training(out):
+    """The reference model in TRAIN mode (dropout rates set to 0, BatchNorm on batch statistics), its own FastSpeech2Loss, the
+    sum of the four losses as in fastspeech2_updater.py:83, torch autograd through the reference's code: the gradients the
+    CUDA training step is checked against (via the oracle), now produced by the reference's wiring."""
+    from oracle import fastspeech2 as ofs
+    from parakeet.models.fastspeech2.fastspeech2 import FastSpeech2, FastSpeech2Loss
+    zero = dict(transformer_enc_dropout_rate=0.0, transformer_enc_positional_dropout_rate=0.0, transformer_enc_attn_dropout_rate=0.0,
+                transformer_dec_dropout_rate=0.0, transformer_dec_positional_dropout_rate=0.0, transformer_dec_attn_dropout_rate=0.0,
+                duration_predictor_dropout_rate=0.0, postnet_dropout_rate=0.0, pitch_predictor_dropout=0.0, pitch_embed_dropout=0.0,
+                energy_predictor_dropout=0.0, energy_embed_dropout=0.0, stop_gradient_from_pitch_predictor=True,
+                stop_gradient_from_energy_predictor=False)
+    ref = FastSpeech2(idim=80, odim=80, **ofs.LJSPEECH_MODEL_CFG, **zero)
+    ref.train()
+    params = ofs.synth_params(1)
+    ref.set_state_dict(params)
+    b = ofs.synth_train_batch(9, [19, 27, 22])
+    for k, v in b.items():
+        out[f"fs2_train_{k}"] = v.numpy()
+    before, after, d_outs, p_outs, e_outs, ys, olens = ref(T(b["text"]), T(b["text_lengths"]), T(b["speech"]), T(b["speech_lengths"]),
+                                                           T(b["durations"]), T(b["pitch"]), T(b["energy"]))
+    l1, dur, pitch, energy = FastSpeech2Loss()(after_outs=after, before_outs=before, d_outs=d_outs, p_outs=p_outs, e_outs=e_outs, ys=ys,
+                                               ds=T(b["durations"]), ps=T(b["pitch"]), es=T(b["energy"]), ilens=T(b["text_lengths"]),
+                                               olens=olens)
+    (l1 + dur + pitch + energy).backward()
+    out["fs2_train_loss"] = np.asarray([float(l1), float(dur), float(pitch), float(energy)], dtype=np.float64)
+    # a representative subset of gradients (all 198 would be 150 MB): every kind of tensor on the path
+    keep = ["encoder.embed.0.weight", "encoder.embed.1.alpha", "encoder.encoders.0.self_attn.linear_q.weight",
+            "encoder.encoders.3.feed_forward.w_1.weight", "encoder.encoders.2.norm1.bias", "encoder.after_norm.weight",
+            "duration_predictor.conv.0.0.weight", "duration_predictor.linear.bias", "pitch_predictor.conv.4.0.bias",
+            "pitch_embed.0.weight", "energy_embed.0.bias", "decoder.embed.0.alpha", "decoder.encoders.1.self_attn.linear_out.weight",
+            "decoder.encoders.3.feed_forward.w_2.bias", "feat_out.weight", "postnet.postnet.0.0.weight", "postnet.postnet.2.1.weight",
+            "postnet.postnet.4.1.bias"]
+    named = dict(ref.named_parameters())
+    for k in keep:
+        gk = named[k].grad
+        gk = (gk if gk is not None else torch.zeros_like(named[k])).detach().reshape(-1)
+        stride = max(1, gk.numel() // 20000)                          # big tensors: every stride-th element + the L2 norm
+        out["fs2_train_grad/" + k] = gk[::stride].numpy()
+        out["fs2_train_gradnorm/" + k] = np.asarray(float(gk.double().norm()))
+    bufs = dict(ref.named_buffers())
+    for k in ("postnet.postnet.0.1._mean", "postnet.postnet.0.1._variance", "postnet.postnet.4.1._variance"):
+        out["fs2_train_stat/" + k] = bufs[k].detach().numpy()
+
+
 def parallel_wavegan(out):
     from oracle import pwg as opwg
     from parakeet.models.parallel_wavegan.parallel_wavegan import PWGGenerator
@@ -204,6 +248,7 @@ def main():
         small, models = {}, {}
         small_pieces(small)
         fastspeech2(models)
+        fastspeech2_training(models)
         parallel_wavegan(models)
         waveflow(models)
         wrappers_and_stft(models)

@@ -305,10 +305,19 @@ def build():
             self.bias = torch.nn.Parameter(torch.zeros(num_features))
             self.register_buffer("_mean", torch.zeros(num_features))
             self.register_buffer("_variance", torch.ones(num_features))
-            self._eps = epsilon
+            self._eps, self._momentum = epsilon, momentum
 
         def forward(self, x):
-            assert not self.training, "only eval-mode BatchNorm is executed through the stand-in"
+            if self.training:
+                # restated Paddle semantics (oracle/README.md): normalise with the biased batch variance; running statistics
+                # move by (1 - momentum) with momentum 0.9 and keep the BIASED variance
+                mean = x.mean(dim=(0, 2))
+                var = x.var(dim=(0, 2), unbiased=False)
+                with torch.no_grad():
+                    self._mean.mul_(self._momentum).add_((1 - self._momentum) * mean)
+                    self._variance.mul_(self._momentum).add_((1 - self._momentum) * var)
+                return (x - mean[None, :, None]) / torch.sqrt(var[None, :, None] + self._eps) * self.weight[None, :, None] \
+                    + self.bias[None, :, None]
             return TF.batch_norm(x, self._mean, self._variance, self.weight, self.bias, False, 0.0, self._eps)
     nn.BatchNorm1D = BatchNorm1D
 
@@ -331,7 +340,7 @@ def build():
             self.p = p
 
         def forward(self, x):
-            assert not self.training or self.p == 0.0, "dropout is only executed in eval mode"
+            assert not self.training or self.p == 0.0, "dropout is only executed with p = 0 or in eval mode (RNG streams differ)"
             return x
     nn.Dropout = Dropout
 
@@ -420,7 +429,10 @@ def build():
     F = types.ModuleType("paddle.nn.functional")
     F.softmax = lambda x, axis=-1: T(torch.softmax(x, dim=axis))
     F.log_softmax = lambda x, axis=-1: T(torch.log_softmax(x, dim=axis))
-    F.dropout = lambda x, p=0.5, training=True, **k: x
+    def f_dropout(x, p=0.5, training=True, **k):
+        assert (not training) or p == 0.0, "F.dropout is only executed with p = 0 or training=False"
+        return x
+    F.dropout = f_dropout
     F.relu = lambda x: T(torch.relu(x))
     F.l1_loss = lambda a, b, reduction="mean": T(TF.l1_loss(a, b, reduction=reduction))
     F.mse_loss = lambda a, b, reduction="mean": T(TF.mse_loss(a, b, reduction=reduction))

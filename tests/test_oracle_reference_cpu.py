@@ -108,3 +108,25 @@ def test_multi_resolution_stft_loss_equals_executed_reference(g):
     from oracle import stft as ostft
     sc, mag = ostft.multi_resolution_stft_loss(torch.from_numpy(g["stft_x"]), torch.from_numpy(g["mrstft_y"]))
     assert np.allclose([float(sc), float(mag)], g["mrstft_loss"], rtol=2e-5)
+
+
+def test_training_forward_loss_and_gradients_equal_executed_reference(g):
+    """The reference model in train mode (dropout 0, BatchNorm on batch statistics) + its FastSpeech2Loss + the updater's loss sum,
+    differentiated by autograd THROUGH THE REFERENCE'S CODE: losses, a representative set of gradients (every kind of tensor on
+    the path; large ones sampled + their norm) and the updated BatchNorm statistics vs oracle.train_step_grads - the reference
+    the CUDA training step is tested against."""
+    from oracle import fastspeech2 as ofs
+    params = ofs.synth_params(1)
+    b = {k: torch.from_numpy(g[f"fs2_train_{k}"]) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+    losses, grads, stats = ofs.train_step_grads(params, None, b)
+    assert np.allclose([losses["l1_loss"], losses["duration_loss"], losses["pitch_loss"], losses["energy_loss"]], g["fs2_train_loss"], rtol=1e-5)
+    keys = [k[len("fs2_train_grad/"):] for k in g.files if k.startswith("fs2_train_grad/")]
+    assert len(keys) == 18
+    for k in keys:
+        ref = torch.from_numpy(g["fs2_train_grad/" + k])
+        mine = grads[k].reshape(-1)
+        stride = max(1, mine.numel() // 20000)
+        assert rel_err(mine[::stride], ref) < 2e-4, k            # fp32 autograd through two orderings of the same graph
+        assert abs(float(mine.double().norm()) - float(g["fs2_train_gradnorm/" + k])) <= 2e-4 * max(float(g["fs2_train_gradnorm/" + k]), 1e-12), k
+    for k in [k for k in g.files if k.startswith("fs2_train_stat/")]:
+        assert rel_err(stats[k[len("fs2_train_stat/"):]], torch.from_numpy(g[k])) < 1e-5, k
