@@ -172,6 +172,21 @@ def parallel_wavegan(out):
         out["pwg_y_weight_norm"] = ref2(T(x), T(c)).numpy()
 
 
+def pwg_discriminator(out):
+    from oracle import pwg as opwg
+    from parakeet.models.parallel_wavegan.parallel_wavegan import PWGDiscriminator
+    cfg = dict(opwg.DEFAULT_DISCRIMINATOR_PARAMS)
+    cfg["use_weight_norm"] = False
+    ref = PWGDiscriminator(**cfg)
+    ref.eval()
+    dp = opwg.synth_discriminator_params(12)
+    out["pwgd_keys"] = np.asarray(check_keys(ref, dp, "PWGDiscriminator"))
+    ref.set_state_dict(dp)
+    x = torch.randn(2, 1, 900, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        out["pwgd_x"], out["pwgd_y"] = x.numpy(), ref(T(x)).numpy()
+
+
 def waveflow(out):
     from oracle import waveflow as owf
     from parakeet.models.waveflow import ConditionalWaveFlow
@@ -250,6 +265,7 @@ def main():
         fastspeech2(models)
         fastspeech2_training(models)
         parallel_wavegan(models)
+        pwg_discriminator(models)
         waveflow(models)
         wrappers_and_stft(models)
     finally:

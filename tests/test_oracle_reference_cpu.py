@@ -130,3 +130,12 @@ def test_training_forward_loss_and_gradients_equal_executed_reference(g):
         assert abs(float(mine.double().norm()) - float(g["fs2_train_gradnorm/" + k])) <= 2e-4 * max(float(g["fs2_train_gradnorm/" + k]), 1e-12), k
     for k in [k for k in g.files if k.startswith("fs2_train_stat/")]:
         assert rel_err(stats[k[len("fs2_train_stat/"):]], torch.from_numpy(g[k])) < 1e-5, k
+
+
+def test_pwg_discriminator_equals_executed_reference(g):
+    from oracle import pwg as opwg
+    dp = opwg.synth_discriminator_params(12)
+    assert sorted(dp) == list(g["pwgd_keys"])
+    with torch.no_grad():
+        y = opwg.discriminator_forward(dp, torch.from_numpy(g["pwgd_x"]))
+    assert rel_err(y, torch.from_numpy(g["pwgd_y"])) < TOL
