@@ -1,7 +1,7 @@
 """CPU emulation of the whole 30-layer generator with frame-rate conditioning (tile-wise band-table x P-window products,
 split-bf16 operands) against the current formulation and fp64: precision of DESIGN.md 7.2 (1.4e-5 vs 1.2e-5)."""
-import sys, math, torch
-sys.path.insert(0,'/root/repo')
+import os, sys, math, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch.nn.functional as F
 from oracle import pwg
 from parakeet_b200.models import _pwg_frame_cond as fc
