@@ -30,11 +30,14 @@ int fail(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
-  static int n = 0;
+  // per device ordinal: a process may drive several devices (grid sizing must follow the CURRENT device)
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -204,7 +204,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
             if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * (kFcStageBytes + kFcPBytes));
             tma_load_3d_2sm_a(st, &tm_u_hi, fb, 0, m0, b * p.u_bmul);
             tma_load_3d_2sm_a(st + kPwgTile, &tm_u_lo, fb, 0, m0, b * p.u_bmul);
-            const int j0 = m0 / p.hop - 2;
+            const int j0 = (m0 / p.hop - 2) & ~7;   // aligned to 8 frames (16 B): TMA faults on an unaligned innermost coordinate
             const uint32_t pb = pbuf + (n_g1 & 1) * kFcPBytes;
             tma_load_3d_2sm_a(pb, &tm_p_hi, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
             tma_load_3d_2sm_a(pb + kFcWTile, &tm_p_lo, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
@@ -514,7 +514,7 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
                a->w2_hi && a->w2_lo && a->bias1 && a->bias2 && a->skip, "NULL pointer in pk_pwg_layer_fc_args");
   PK_CHECK_ARG(a->x_hi != a->y_hi, "layer output must not alias its input");
   PK_CHECK_ARG(a->u_batches == 1 || a->u_batches == a->batch, "u_batches must be 1 or batch");
-  PK_CHECK_ARG(a->p_rows > 0 && a->p_row0 >= 0 && a->p_row0 + 128 <= a->p_rows && (a->p_ld % 8) == 0 && a->p_frames > 0 &&
+  PK_CHECK_ARG(a->p_rows > 0 && a->p_row0 >= 0 && a->p_row0 + 128 <= a->p_rows && (a->p_ld % 8) == 0 && a->p_ld >= 64 && a->p_frames > 0 &&
                a->p_frames <= a->p_ld, "bad P plane geometry");
   PK_CHECK_ARG(sm_count() >= 2, "needs at least one SM pair");
   CUtensorMap tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
@@ -527,8 +527,9 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   if ((rc = encode_tmap_bf16_3d(&tu_lo, a->u_lo, 64, T, a->u_batches, 64, T * 64, 128))) return rc;
   // P planes (batch, p_rows, p_ld): frames are the K axis; columns >= p_frames (and < 0) read as zero
   const uint64_t prow = a->p_rows, pld = a->p_ld;
-  if ((rc = encode_tmap_bf16_3d(&tp_hi, a->p_hi, a->p_frames, prow, B, pld, prow * pld, 64))) return rc;
-  if ((rc = encode_tmap_bf16_3d(&tp_lo, a->p_lo, a->p_frames, prow, B, pld, prow * pld, 64))) return rc;
+  // (the extent is the padded row length p_ld >= 64: columns [p_frames, p_ld) hold zeros in memory, frames < 0 are out of bounds)
+  if ((rc = encode_tmap_bf16_3d(&tp_hi, a->p_hi, pld, prow, B, pld, prow * pld, 64))) return rc;
+  if ((rc = encode_tmap_bf16_3d(&tp_lo, a->p_lo, pld, prow, B, pld, prow * pld, 64))) return rc;
   const uint64_t k1 = 5 * kChunkK;     // row pitch of the packed W1 (pk_pwg_residual_layer layout); only the 3 tap chunks are read
   if ((rc = encode_tmap_bf16_3d(&tw1_hi, a->w1_hi, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;
   if ((rc = encode_tmap_bf16_3d(&tw1_lo, a->w1_lo, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;

@@ -35,9 +35,11 @@ class GraphRunner:
             return fn(*inputs)
         ent = self._graphs.get(key)
         if ent is None:
-            if key not in self._seen or len(self._graphs) >= self.max_graphs:
+            if key not in self._seen:
                 self._seen.add(key)
                 return fn(*inputs)
+            if len(self._graphs) >= self.max_graphs:      # LRU: drop the least recently replayed graph (and its memory pool)
+                self._graphs.pop(next(iter(self._graphs)))
             static_in = [t.clone() for t in inputs]
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -50,6 +52,7 @@ class GraphRunner:
                 return fn(*inputs)
             ent = (graph, static_in, out)
             self._graphs[key] = ent
+        self._graphs[key] = self._graphs.pop(key)       # most recently used last
         graph, static_in, out = ent
         for s, t in zip(static_in, inputs):
             s.copy_(t)

@@ -49,7 +49,10 @@ class Layer:
             v = torch.as_tensor(v)
             if tuple(v.shape) != tuple(self._params[k].shape):
                 raise ValueError(f"shape mismatch for {k}: got {tuple(v.shape)}, expected {tuple(self._params[k].shape)}")
-            self._register(k, v)
+            cur = self._params[k]
+            # in place: a training step may have turned the parameters into views of its flat buffer (training/flat.py);
+            # re-registering fresh tensors would silently detach the model from the optimiser's storage
+            cur.copy_(v.detach().to(device=cur.device, dtype=cur.dtype))
         self._packed = None
 
     load_dict = set_state_dict  # paddle alias

@@ -8,7 +8,7 @@ alike, so the 1x1 aux convolution of a residual block (:300-303) commutes with i
 U (T x frames) is banded: row t has at most 4 non-zero frames starting at t // hop - 2, it repeats with period hop away from
 the ends of the utterance, and the zero-padding of the FIR stages only changes rows within 95 samples of either end
 (scripts/ptrick_study.py).  A 128-sample tile starting at t0 therefore needs the K = 16 frames j0 .. j0 + 15,
-j0 = t0 // hop - 2, and its A operand is the "tile-relative band table": row t holds U[t, j0(tile of t) + k], k < 16.
+j0 = floor8(t0 // hop - 2) (the window start is aligned to 8 frames = 16 bytes for TMA), and its A operand is the "tile-relative band table": row t holds U[t, j0(tile of t) + k], k < 16.
 This module builds that table on the host (constants of the model, computed once per utterance length); the layer kernel
 multiplies it with the matching window of P, frames outside [0, frames) reading as zero (TMA out-of-bounds fill).
 """
@@ -18,6 +18,11 @@ import torch.nn.functional as F
 TILE = 128
 KWIN = 16
 EDGE = 128          # rows next to either end of an utterance that carry their own coefficients (edge effects reach < 128)
+
+
+def window_start(t0, hop):
+    """First frame of the 16-frame K window of the tile starting at sample t0 (python ints or tensors): floor8(t0 // hop - 2)."""
+    return (t0 // hop - 2) // 8 * 8
 
 
 def upsample_operator(firs, scales, frames):
@@ -41,7 +46,7 @@ def _row_windows(U, hop, width):
 
 
 def tile_band_table(firs, scales, frames, width=8):
-    """(frames * hop, KWIN) float64: row t = U[t, j0 + k] with j0 = (t // TILE * TILE) // hop - 2 (tile-relative window)."""
+    """(frames * hop, KWIN) float64: row t = U[t, j0 + k] with j0 = window_start(t // TILE * TILE, hop) (tile-relative window)."""
     hop = 1
     for s in scales:
         hop *= s
@@ -57,8 +62,10 @@ def tile_band_table(firs, scales, frames, width=8):
         rows[:EDGE] = ref[:EDGE]
         rows[T - EDGE:] = ref[ref_frames * hop - EDGE:]
     t = torch.arange(T)
-    shift = (t // hop - 2) - ((t // TILE * TILE) // hop - 2)            # 0 or 1 (a tile is shorter than a hop)
-    assert int(shift.max()) + width <= KWIN
+    # the kernel's K window starts at window_start(t0) = floor8(t0 // hop - 2): TMA needs the innermost coordinate of a box
+    # 16-byte aligned (8 bf16 frames) - an unaligned start raises an illegal-instruction fault on sm_100a
+    shift = (t // hop - 2) - window_start(t // TILE * TILE, hop)        # 0 .. 8
+    assert int(shift.min()) >= 0 and int(shift.max()) + width <= KWIN
     out = torch.zeros(T, KWIN, dtype=torch.float64)
     out.scatter_(1, shift[:, None] + torch.arange(width)[None, :], rows)
     return out

@@ -282,7 +282,7 @@ class PWGGenerator(Layer):
         if frame_lens is not None:
             ops.mask_rows_(m1, frame_lens)                               # frames past an utterance's end contribute nothing
         m1s = Split.from_f32(m1)
-        Fp = (frames + 7) // 8 * 8
+        Fp = max((frames + 7) // 8 * 8, 64)
         P = Split.zeros((B, NL * 128, Fp), self.device)
         a_spec = dict(rows=NL * 128, cols=A, ld=A, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
         b_spec = dict(rows=frames, cols=A, ld=A, batch_stride=frames * A, batches=B, bmul=1, hmul=0, col0=0, colh=0)

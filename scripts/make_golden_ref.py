@@ -203,6 +203,13 @@ def waveflow(out):
         out["wf_mel"], out["wf_z"] = mel.numpy(), z.numpy()
         out["wf_cond"] = cond.numpy()
         out["wf_x"] = ref.decoder.inverse(T(z), cond).numpy()
+        # second vector: 22 mel frames -> W = 335 columns > 2 x 128, so the +-128 width taps of layer 7 land on live data
+        # (the 9-frame vector above has W = 127: its widest taps only ever see zero padding)
+        mel2 = torch.randn(1, 80, 22, generator=g) * 0.5 - 3
+        cond2 = ref.encoder(T(mel2), trim_conv_artifact=True)
+        z2 = torch.randn(1, cond2.shape[-1], generator=g)
+        out["wf2_mel"], out["wf2_z"] = mel2.numpy(), z2.numpy()
+        out["wf2_x"] = ref.decoder.inverse(T(z2), cond2).numpy()
 
 
 def wrappers_and_stft(out):

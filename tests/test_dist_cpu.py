@@ -93,7 +93,8 @@ def _train_exchange_worker(rank, world, port, q):
         fb.flat.copy_(new_p)
         # the flat update equals the per-tensor update with the mean gradient (padding lanes carry zero gradient)
         ok = ok and all(torch.allclose(params[k], per_tensor[k], atol=1e-7) for k in fb.names)
-        q.put((rank, ok, params["w1"].clone(), params["w2"].clone()))
+        # plain Python lists: a tensor on an mp queue is sent as a handle to shared storage that dies with this process
+        q.put((rank, ok, params["w1"].tolist(), params["w2"].tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -112,7 +113,8 @@ def test_two_rank_gloo_training_exchange():
         p.join(timeout=60)
     assert all(o[1] for o in out)
     # every rank applied the same update: replicas stay bit-identical, and the weights moved
-    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
     g = torch.Generator().manual_seed(0)
     w1_init = torch.randn(5, 3, generator=g)
-    assert not torch.equal(out[0][2], w1_init) and (out[0][2] - w1_init).abs().max() < 2e-3   # |step| <= lr for the first Adam step
+    w1_new = torch.tensor(out[0][2])
+    assert not torch.equal(w1_new, w1_init) and (w1_new - w1_init).abs().max() < 2e-3   # |step| <= lr for the first Adam step

@@ -188,6 +188,51 @@ def test_waveflow_inference_vs_oracle(cuda):
     assert rel_err(out, ref) < TOL
 
 
+def test_waveflow_wide_rows_vs_oracle(cuda):
+    """W = 431 columns (28 mel frames): every width dilation up to 128 reaches live columns on both sides; odd batch."""
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    params = owf.synth_params(4)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m.set_state_dict(params)
+    folded = owf.fold_weight_norm(params)
+    g = torch.Generator().manual_seed(41)
+    mel = torch.randn(3, 80, 28, generator=g) * 0.5 - 3
+    z = torch.randn(3, 256 * 28 - 272, generator=g)
+    with torch.no_grad():
+        ref = owf.infer(folded, mel, z)
+    out = m.infer(mel.to(cuda), z=z.to(cuda))
+    assert list(out.shape) == list(ref.shape) and rel_err(out, ref) < TOL
+
+
+def test_waveflow_cfg4_full_size_properties(cuda):
+    """cfg4 (B=16, 400 mel frames -> 16 x 102 128 samples, W = 6383): batch independence bit for bit, determinism / graph
+    replay == eager, and one whole utterance against the oracle (mirror of test_pwg_full_size_properties)."""
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    params = owf.synth_params(4)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m.set_state_dict(params)
+    folded = owf.fold_weight_norm(params)
+    g = torch.Generator().manual_seed(42)
+    mel = (torch.randn(16, 80, 400, generator=g) * 0.5 - 3).to(cuda)
+    t_c = 256 * 400 - 272
+    z = torch.randn(16, t_c, generator=g).to(cuda)
+    y0 = m.infer(mel, z=z).clone()                                  # eager
+    assert list(y0.shape) == [16, t_c // 16 * 16] and torch.isfinite(y0).all()
+    y1 = m.infer(mel, z=z).clone()                                  # capture
+    y2 = m.infer(mel, z=z).clone()                                  # replay
+    assert m._graphs.replays >= 1
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    one = m.infer(mel[5:6].contiguous(), z=z[5:6].contiguous())     # utterance 5 alone == inside the batch
+    assert torch.equal(one[0], y0[5])
+    # one whole utterance against the oracle (the row recurrence spreads every input over the full width, so a truncated
+    # oracle run is not comparable; the full-width run costs ~1 TFLOP on the host)
+    with torch.no_grad():
+        ref = owf.infer(folded, mel[:1].cpu(), z[:1].cpu())
+    assert rel_err(y0[0], ref[0]) < TOL
+
+
 def test_fs2_loss_vs_oracle(cuda, fs2):
     """FastSpeech2Loss (use_masking=True) on the teacher-forced forward of the golden batch."""
     from oracle import fastspeech2 as ofs

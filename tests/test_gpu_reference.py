@@ -60,3 +60,7 @@ def test_waveflow_cuda_vs_executed_reference(cuda, g):
     assert rel_err(wf.encode(mel), torch.from_numpy(g["wf_cond"])) < 1e-4
     out = wf.infer(mel, z=z)
     assert tuple(out.shape) == g["wf_x"].shape and rel_err(out, torch.from_numpy(g["wf_x"])) < TOL
+    # W = 335 columns: the +-128 taps of the widest layer are inside the row (the vector above has W = 127)
+    mel2, z2 = torch.from_numpy(g["wf2_mel"]).to(cuda), torch.from_numpy(g["wf2_z"]).to(cuda)
+    out2 = wf.infer(mel2, z=z2)
+    assert tuple(out2.shape) == g["wf2_x"].shape and rel_err(out2, torch.from_numpy(g["wf2_x"])) < TOL

@@ -258,7 +258,7 @@ def test_weight_norm_fold_equals_torch_weight_norm_and_train_bn_equals_torch_bat
 
 def test_pwg_frame_rate_conditioning_tables_reproduce_the_aux_path():
     """DESIGN 7.2 groundwork: conv1x1_aux(upsample(m')) == band_table_tile @ (W_aux m')[window], tile by tile, with exactly the
-    index conventions the layer kernel will use (window start t0 // hop - 2, frames outside [0, frames) read as zero)."""
+    index conventions the layer kernel uses (window start floor8(t0 // hop - 2), frames outside [0, frames) read as zero)."""
     from oracle import pwg as opwg
     from parakeet_b200.models import _pwg_frame_cond as fc
     cfg = opwg.DEFAULT_GENERATOR_PARAMS
@@ -281,7 +281,7 @@ def test_pwg_frame_rate_conditioning_tables_reproduce_the_aux_path():
         Ppad[fc.KWIN:fc.KWIN + frames] = P
         worst = 0.0
         for t0 in range(0, T, fc.TILE):
-            j0 = t0 // hop - 2
+            j0 = fc.window_start(t0, hop)
             win = Ppad[fc.KWIN + j0:fc.KWIN + j0 + fc.KWIN]                           # zero outside [0, frames)
             got = table[t0:t0 + fc.TILE] @ win
             worst = max(worst, float((got - ref[t0:t0 + fc.TILE]).abs().max()))

@@ -81,6 +81,12 @@ def test_waveflow_oracle_equals_executed_reference(g):
         x = owf.infer(folded, mel, z)
     assert rel_err(cond, torch.from_numpy(g["wf_cond"])) < 1e-5
     assert tuple(x.shape) == g["wf_x"].shape and rel_err(x, torch.from_numpy(g["wf_x"])) < 1e-5
+    # 22 mel frames: W = 335 > 2 x 128, the widest (+-128) width taps of layer 7 read live columns in the reference
+    mel2, z2 = torch.from_numpy(g["wf2_mel"]), torch.from_numpy(g["wf2_z"])
+    assert z2.shape[-1] // 16 > 2 * 128
+    with torch.no_grad():
+        x2 = owf.infer(folded, mel2, z2)
+    assert tuple(x2.shape) == g["wf2_x"].shape and rel_err(x2, torch.from_numpy(g["wf2_x"])) < 1e-5
 
 
 def test_inference_wrappers_and_stft_equal_executed_reference(g):
