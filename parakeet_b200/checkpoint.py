@@ -79,3 +79,21 @@ def load_stats(path):
     if stat.ndim != 2 or stat.shape[0] != 2:
         raise ValueError(f"{path}: expected np.stack([mean, scale]) of shape (2, n_mels), got {stat.shape}")
     return stat[0].astype(np.float32), stat[1].astype(np.float32)
+
+
+def save(obj, path):
+    """`paddle.save(obj, path)` for nested dicts of arrays / tensors / scalars (snapshot_iter_*.pdz: updater.state_dict(),
+    step-N.pdparams: model.state_dict()): every tensor is stored as a plain numpy array, pickle protocol 2 like Paddle 2.1.
+    `load()` above (and `paddle.load`, which passes ndarrays through) reads it back."""
+    import torch
+
+    def conv(o):
+        if torch.is_tensor(o):
+            return o.detach().cpu().numpy()
+        if isinstance(o, dict):
+            return OrderedDict((k, conv(v)) for k, v in o.items())
+        if isinstance(o, (list, tuple)):
+            return type(o)(conv(v) for v in o)
+        return o
+    with open(path, "wb") as f:
+        pickle.dump(conv(obj), f, protocol=2)

@@ -204,7 +204,9 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
             if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * (kFcStageBytes + kFcPBytes));
             tma_load_3d_2sm_a(st, &tm_u_hi, fb, 0, m0, b * p.u_bmul);
             tma_load_3d_2sm_a(st + kPwgTile, &tm_u_lo, fb, 0, m0, b * p.u_bmul);
-            const int j0 = (m0 / p.hop - 2) & ~7;   // aligned to 8 frames (16 B): TMA faults on an unaligned innermost coordinate
+            // one K window per PAIR tile (the two CTAs supply the two halves of the same B operand): it starts at the frame of
+            // the pair's first row, aligned down to 8 frames (16 B) - TMA faults on an unaligned innermost coordinate
+            const int j0 = ((m0 - 128 * static_cast<int>(rank)) / p.hop - 2) & ~7;
             const uint32_t pb = pbuf + (n_g1 & 1) * kFcPBytes;
             tma_load_3d_2sm_a(pb, &tm_p_hi, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
             tma_load_3d_2sm_a(pb + kFcWTile, &tm_p_lo, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);

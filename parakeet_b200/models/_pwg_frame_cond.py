@@ -7,7 +7,7 @@ alike, so the 1x1 aux convolution of a residual block (:300-303) commutes with i
 
 U (T x frames) is banded: row t has at most 4 non-zero frames starting at t // hop - 2, it repeats with period hop away from
 the ends of the utterance, and the zero-padding of the FIR stages only changes rows within 95 samples of either end
-(scripts/ptrick_study.py).  A 128-sample tile starting at t0 therefore needs the K = 16 frames j0 .. j0 + 15,
+(scripts/ptrick_study.py).  A 256-sample pair tile starting at t0 therefore needs the K = 16 frames j0 .. j0 + 15,
 j0 = floor8(t0 // hop - 2) (the window start is aligned to 8 frames = 16 bytes for TMA), and its A operand is the "tile-relative band table": row t holds U[t, j0(tile of t) + k], k < 16.
 This module builds that table on the host (constants of the model, computed once per utterance length); the layer kernel
 multiplies it with the matching window of P, frames outside [0, frames) reading as zero (TMA out-of-bounds fill).
@@ -15,7 +15,7 @@ multiplies it with the matching window of P, frames outside [0, frames) reading 
 import torch
 import torch.nn.functional as F
 
-TILE = 128
+TILE = 256          # rows of a CTA-pair tile: both CTAs of the pair multiply with the SAME 16-frame window of P
 KWIN = 16
 EDGE = 128          # rows next to either end of an utterance that carry their own coefficients (edge effects reach < 128)
 

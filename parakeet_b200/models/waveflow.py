@@ -195,6 +195,25 @@ class ConditionalWaveFlow(Layer):
         fn = lambda m_, z_: self.inverse(z_, self.encode(m_, trim_conv_artifact=True))
         return self._graphs.run(("infer", B, frames), fn, [mel, z.contiguous().float()]).clone()
 
+    @classmethod
+    def from_pretrained(cls, config, checkpoint_path, device=None):
+        """reference :827-852: build from a config (attribute or mapping access: config.model.*, config.data.n_mels) and load
+        `checkpoint_path + ".pdparams"` (utils/checkpoint.py:load_parameters appends the extension) without PaddlePaddle."""
+        import os
+        from .. import checkpoint
+
+        def get(node, key):
+            return node[key] if isinstance(node, dict) else getattr(node, key)
+        mc, dc = get(config, "model"), get(config, "data")
+        model = cls(upsample_factors=list(get(mc, "upsample_factors")), n_flows=get(mc, "n_flows"), n_layers=get(mc, "n_layers"),
+                    n_group=get(mc, "n_group"), channels=get(mc, "channels"), n_mels=get(dc, "n_mels"),
+                    kernel_size=tuple(get(mc, "kernel_size")), device=device)
+        path = str(checkpoint_path)
+        if not os.path.exists(path) and os.path.exists(path + ".pdparams"):
+            path = path + ".pdparams"
+        model.set_state_dict(checkpoint.load(path))
+        return model
+
     def predict(self, mel):
         """reference :807-825: numpy mel (n_mels, T') -> numpy audio."""
         mel = torch.as_tensor(np.asarray(mel), dtype=torch.float32, device=self.device).unsqueeze(0)

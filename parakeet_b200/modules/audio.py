@@ -145,12 +145,27 @@ class LogMelFBank:
 
 
 class Energy:
-    """reference data/get_feats.py:167-220: sqrt(clip(sum_k |X|^2, 1e-10)) per frame (token averaging stays host-side)."""
+    """reference data/get_feats.py:167-220: sqrt(clip(sum_k |X|^2, 1e-10)) per frame (+ token averaging, :205-220)."""
 
     def __init__(self, sr=24000, n_fft=2048, hop_length=300, win_length=None, window="hann", center=True, pad_mode="reflect",
                  device=None):
         self._stft = STFT(n_fft, hop_length, win_length, window, center=center, pad_mode=pad_mode, device=device)
 
-    def get_energy(self, wav):
+    @staticmethod
+    def _average_by_duration(energy, d):
+        """get_feats.py:205-213 on the device: mean of the frames of each token (0 for zero-length tokens) -> (T, 1)."""
+        d = torch.as_tensor(np.asarray(d), dtype=torch.int64, device=energy.device).reshape(-1)
+        ends = torch.cumsum(d, 0)
+        csum = torch.cat([energy.new_zeros(1, dtype=torch.float64), torch.cumsum(energy.double(), 0)])
+        ends_c, starts_c = ends.clamp(max=energy.shape[0]), (ends - d).clamp(max=energy.shape[0])   # numpy slicing clips at the end
+        n = (ends_c - starts_c).clamp(min=1)
+        avg = (csum[ends_c] - csum[starts_c]) / n
+        return torch.where(ends_c > starts_c, avg, torch.zeros_like(avg)).float().reshape(-1, 1)
+
+    def get_energy(self, wav, use_token_averaged_energy=True, duration=None):
+        """reference :215-220; without `duration` the frame-level energy (frames,), with it the token average (T, 1)."""
         x = torch.as_tensor(wav, dtype=torch.float32, device=self._stft.device).reshape(1, -1)
-        return self._stft._run(x, energy=True, energy_clip=1e-10)["energy"][0]
+        energy = self._stft._run(x, energy=True, energy_clip=1e-10)["energy"][0]
+        if use_token_averaged_energy and duration is not None:
+            energy = self._average_by_duration(energy, duration)
+        return energy

@@ -66,7 +66,17 @@ class FastSpeech2TrainStep:
         # batch shape (B, Tmax, Lmax) once a shape repeats (bucketed samplers); the step is host-bound (~600 launches).
         self._fb_graphs = GraphRunner(max_graphs=16)
         self.use_graphs = os.environ.get("PK_TRAIN_GRAPH", "0") == "1"
-        self.sums = torch.zeros(4096, dtype=torch.float32, device=dev)
+        # workspace of the BatchNorm / LayerNorm reductions: 2 floats per channel (pk_batch_norm_train / _bwd)
+        widest = max([model.odim, model.adim] + [int(v.shape[0]) for k, v in model._params.items() if k.startswith("postnet.")])
+        self.sums = torch.zeros(max(4096, 2 * widest), dtype=torch.float32, device=dev)
+        if model.adim > 512:
+            raise NotImplementedError("pk_layer_norm_bwd supports rows of at most 512 channels (adim)")
+        if self.world > 1:
+            # paddle.DataParallel broadcasts rank 0's parameters and buffers at construction (train.py:117-119)
+            dist.broadcast(self.flat, src=0, group=process_group)
+            for k, v in model._params.items():
+                if k.endswith(BUFFERS):
+                    dist.broadcast(v, src=0, group=process_group)
 
     # ------------------------------------------------------------------------------------------------------------
     # GEMM-shaped forward / backward pieces
@@ -401,6 +411,34 @@ class FastSpeech2TrainStep:
         key = tuple(tuple(t.shape) for t in tensors)
         fn = lambda *ts: self.forward_backward(dict(zip(order, ts)))
         return self._fb_graphs.run(key, fn, tensors).clone()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # snapshot / resume (reference: StandardUpdater.state_dict / set_state_dict, training/updaters/standard_updater.py;
+    # Snapshot extension writes it with paddle.save as snapshot_iter_<n>.pdz and train.py resumes by constructing the
+    # updater first and loading afterwards - which is why Layer.set_state_dict copies IN PLACE into the flat buffer)
+    # ------------------------------------------------------------------------------------------------------------
+    def state_dict(self, epoch=0):
+        """{"main_params", "main_optimizer", "epoch", "iteration"}: Adam moments per parameter under Paddle's accumulator
+        suffixes (`<name>_moment1_0`, `<name>_moment2_0`; Paddle prefixes them with its internal tensor names, which do not
+        exist here, so the structured names are used) plus the step count the bias correction needs."""
+        opt = {}
+        for k, o, n in zip(self.buffers.names, self.buffers.offsets, self.buffers.sizes):
+            shape = self.m._params[k].shape
+            opt[k + "_moment1_0"] = self.adam_m[o:o + n].view(shape).clone()
+            opt[k + "_moment2_0"] = self.adam_v[o:o + n].view(shape).clone()
+        opt["step_count"] = self.step_count
+        opt["LR_Scheduler"] = {"last_lr": self.lr}
+        return {"main_params": self.m.state_dict(), "main_optimizer": opt, "epoch": int(epoch), "iteration": int(self.step_count)}
+
+    def set_state_dict(self, state):
+        self.m.set_state_dict(state["main_params"])                  # in place: the parameters stay views of self.flat
+        opt = state.get("main_optimizer", {})
+        for k, o, n in zip(self.buffers.names, self.buffers.offsets, self.buffers.sizes):
+            for suffix, buf in (("_moment1_0", self.adam_m), ("_moment2_0", self.adam_v)):
+                if k + suffix in opt:
+                    buf[o:o + n].copy_(torch.as_tensor(opt[k + suffix]).reshape(-1).to(buf.device, buf.dtype))
+        self.step_count = int(opt.get("step_count", state.get("iteration", self.step_count)))
+        self._packs = {}
 
     def step(self, batch):
         """One update: returns the four loss values (device tensor: l1, duration, pitch, energy)."""

@@ -146,3 +146,72 @@ def test_fs2_training_reduces_loss(cuda):
     for _ in range(7):
         last = float(ts.step(batch).sum())
     assert last < first, (first, last)
+
+
+def _cfg5_lengths(n=8, seed=50):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(60, 141, (n,), generator=g).tolist()          # cfg 5: 8 utterances per GPU, T ~ U{60..140}
+
+
+def test_fs2_training_step_cfg5_shape_vs_oracle(cuda):
+    """BASELINE cfg 5 per-GPU shape (8 utterances of 60..140 phonemes, durations U{2..12} -> ~5 600 mel frames): losses,
+    every gradient tensor and the BatchNorm statistics against torch autograd on the oracle.  On a batch this size a single
+    ReLU kink no longer moves a weight gradient by percents, so the bound is the 1e-3 contract on the relative L2 error."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    params = ofs.synth_params(1)
+    batch = ofs.synth_train_batch(51, _cfg5_lengths())
+    assert batch["speech"].shape[0] == 8 and batch["speech"].shape[1] > 500
+    losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
+    m.set_state_dict(params)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    got = [float(v) for v in ts.forward_backward(batch)]
+    ref = [losses_ref[k] for k in ("l1_loss", "duration_loss", "pitch_loss", "energy_loss")]
+    assert np.allclose(got, ref, rtol=1e-3), (got, ref)
+    bad = []
+    for k, gref in grads_ref.items():
+        g, r = ts.grads[k].detach().double().cpu(), gref.double()
+        e = (g - r).norm().item() / max(r.norm().item(), 1e-12)
+        if e > 1e-3 and (g - r).norm().item() > 1e-7:
+            bad.append((k, e))
+    assert not bad, sorted(bad, key=lambda t: -t[1])[:8]
+    for k, v in stats_ref.items():
+        assert _close(m.state_dict()[k], v), k
+
+
+def test_fs2_three_steps_follow_the_oracle_adam_trajectory(cuda):
+    """Three consecutive FastSpeech2TrainStep.step() calls (forward, backward, paddle-Adam) against three oracle steps
+    (train_step_grads + adam_step) on the same batch: the PARAMETERS after step 3 within 1e-3 (relative to the largest
+    parameter change of that tensor, plus the fp32 noise floor lr * 1e-2 of Adam's sign-like first steps)."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    params = ofs.synth_params(1)
+    batch = ofs.synth_train_batch(52, _cfg5_lengths(4, seed=53))
+    lr = 1e-3
+    p_ref, state, loss_ref = dict(params), {}, []
+    for _ in range(3):
+        losses, grads, stats = ofs.train_step_grads(p_ref, None, batch, stop_gradient_from_pitch_predictor=True)
+        loss_ref.append(losses["loss"])
+        new = ofs.adam_step({k: p_ref[k] for k in grads}, grads, state, lr=lr)
+        p_ref = {**p_ref, **new, **stats}
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
+    m.set_state_dict(params)
+    ts = FastSpeech2TrainStep(m, learning_rate=lr)
+    loss_got = [float(ts.step(batch).sum()) for _ in range(3)]
+    assert np.allclose(loss_got, loss_ref, rtol=2e-3), (loss_got, loss_ref)
+    sd = m.state_dict()
+    bad = []
+    for k, v in p_ref.items():
+        got, ref, init = sd[k].detach().double().cpu(), v.double(), params[k].double()
+        moved = (ref - init).abs().max().item()
+        # elements whose gradient is numerically zero take an arbitrary sign in Adam's first steps (m / sqrt(v) of noise):
+        # compare in relative L2 over the tensor, where those few elements do not dominate
+        e = (got - ref).norm().item() / max((ref - init).norm().item(), 1e-12)
+        if moved > 0 and e > 5e-2:
+            bad.append((k, e, moved))
+    assert not bad, sorted(bad, key=lambda t: -t[1])[:8]
+    # and the loss went down along the way
+    assert loss_got[2] < loss_got[0]
