@@ -145,7 +145,7 @@ int pk_length_regulate(const float* x, const int64_t* dur, int32_t batch, int32_
  * UpsampleNet.forward (:119-138): per scale s, nearest stretch x s (Stretch2D :48-63) then a (1, 2s+1) FIR with zero
  * padding s.  mel: device fp32 (batch, aux, frames + 2*window), channel-first like the reference;
  * conv_in_w: device fp32 [aux][aux][2*window+1]; fir: HOST fp32, the n_stages FIRs concatenated (2*s_k+1 taps each);
- * scales: HOST int32 [n_stages].  Outputs (either may be NULL): c_f32 (batch, aux, T) channel-first fp32 and
+ * scales: HOST int32 [n_stages].  Outputs (either or BOTH may be NULL - then only conv_in_ws is produced, which is all the frame-rate path needs): c_f32 (batch, aux, T) channel-first fp32 and
  * c_hi/c_lo (batch, T, aux) channels-last split-bf16, T = frames * prod(scales).  frame_lens (device int32 [batch] or
  * NULL): valid frames per utterance of a ragged batch; each utterance is then upsampled exactly as if alone
  * (zero padding at its own end) and its samples past frame_lens[b]*hop are written as zero.
@@ -189,15 +189,20 @@ typedef struct pk_pwg_layer_args {
 } pk_pwg_layer_args;
 int pk_pwg_residual_layer(const pk_pwg_layer_args* args, pk_stream_t stream);
 
-/* EXPERIMENTAL (not used by default; PK_PWG_FRAME_COND=1 in the Python model): pk_pwg_residual_layer with frame-rate
- * conditioning.  The upsampling network is linear and per channel, so conv1x1_aux(upsample(m'))[t, n] =
+/* ResidualBlock with FRAME-RATE CONDITIONING (the default residual-stack path of the Python model; PK_PWG_FRAME_COND=0
+ * selects pk_pwg_residual_layer).  The upsampling network is linear and per channel, so conv1x1_aux(upsample(m'))[t, n] =
  * sum_j U[t, j] * P[j, n] with P = conv1x1_aux applied to m' = conv_in(mel) at FRAME rate.  Instead of the sample-rate
- * conditioning planes the kernel takes
- *   u_hi / u_lo: the tile-relative band table of U as split planes (u_batches, t, 64): row t holds U[t, j0 + k] in column
- *                k < 16 (zeros after), j0 = ((t / 128) * 128) / hop - 2; u_batches = 1 (shared) or batch;
- *   p_hi / p_lo: P as split planes (batch, p_rows, p_ld) with frames along the last axis (p_frames valid columns); this
- *                layer's 128 output channels are rows [p_row0, p_row0 + 128).
- * w1 / w2 / bias1 / bias2 / skip / lens as in pk_pwg_layer_args (the aux columns of w1 are not read).  hop >= 128. */
+ * conditioning planes (1.2 GB at cfg 2) the kernel takes
+ *   u_hi / u_lo: the COMPACT band table of U as split planes (u_rows, 64) from ONE allocation (lo after hi): a row holds
+ *                U[t, j0 + k] in column k < 16 (zeros after), j0 = floor8(((t / 256) * 256) / hop - 2) (the K window of
+ *                the 256-sample pair tile of t).  Rows [0, u_period): interior rows by t mod u_period; rows
+ *                [u_start_row, +128): the first 128 samples of any utterance; rows [u_end_base + 384 b, +384): the half
+ *                tiles of utterance b from 128 * ((len_b - 128) / 128) on (zero at and past len_b).  Built by
+ *                parakeet_b200/models/_pwg_frame_cond.py: compact_band_tables (lookup: source_row).
+ *   p_hi / p_lo: P as split planes (batch, p_rows, p_ld), one allocation, frames along the last axis (p_frames valid
+ *                columns, zeros up to p_ld >= 64); this layer's 128 output channels are rows [p_row0, p_row0 + 128).
+ * x / y planes: one allocation each (lo after hi) so that a tile of both planes is ONE 4-D TMA box.
+ * w1 / w2 / bias1 / bias2 / skip / lens as in pk_pwg_layer_args (the aux columns of w1 are not read).  hop >= 256. */
 typedef struct pk_pwg_layer_fc_args {
   int32_t batch, t, dilation, hop;
   const int32_t* lens;
@@ -207,7 +212,7 @@ typedef struct pk_pwg_layer_fc_args {
   void* y_lo;
   const void* u_hi;
   const void* u_lo;
-  int32_t u_batches;
+  int32_t u_rows, u_period, u_start_row, u_end_base;
   int32_t p_rows, p_ld, p_frames, p_row0;
   const void* p_hi;
   const void* p_lo;

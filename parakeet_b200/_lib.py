@@ -68,7 +68,8 @@ class PwgLayerArgs(C.Structure):
 class PwgLayerFcArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("t", C.c_int32), ("dilation", C.c_int32), ("hop", C.c_int32), ("lens", C.c_void_p),
                 ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p), ("u_hi", C.c_void_p),
-                ("u_lo", C.c_void_p), ("u_batches", C.c_int32), ("p_rows", C.c_int32), ("p_ld", C.c_int32),
+                ("u_lo", C.c_void_p), ("u_rows", C.c_int32), ("u_period", C.c_int32), ("u_start_row", C.c_int32),
+                ("u_end_base", C.c_int32), ("p_rows", C.c_int32), ("p_ld", C.c_int32),
                 ("p_frames", C.c_int32), ("p_row0", C.c_int32), ("p_hi", C.c_void_p), ("p_lo", C.c_void_p),
                 ("w1_hi", C.c_void_p), ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p),
                 ("bias1", C.c_void_p), ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]

@@ -1267,7 +1267,7 @@ extern "C" int pk_pwg_upsample(const float* mel, const float* conv_in_w, const f
   PK_CHECK_ARG(mel && conv_in_w && fir && scales && conv_in_ws, "NULL pointer");
   PK_CHECK_ARG(n_stages >= 1 && n_stages <= kUpMaxStages, "n_stages must be in [1,%d]", kUpMaxStages);
   PK_CHECK_ARG(batch > 0 && aux > 0 && frames > 0 && window >= 0, "bad sizes");
-  PK_CHECK_ARG(c_f32 || c_hi, "no output requested");
+  // c_f32 == c_hi == NULL: conv_in only (frame-rate conditioning, pk_pwg_residual_layer_fc, needs no sample-rate tensor)
   PK_CHECK_ARG((c_hi == nullptr) == (c_lo == nullptr), "c_hi and c_lo must both be set or both NULL");
   PK_CHECK_ARG((aux % 8) == 0, "aux must be a multiple of 8 (got %d)", aux);
   UpsampleArgs a;
@@ -1298,6 +1298,7 @@ extern "C" int pk_pwg_upsample(const float* mel, const float* conv_in_w, const f
     PK_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
+  if (c_f32 == nullptr && c_hi == nullptr) return PK_OK;
   size_t floats = 0;
   {
     int w = a.hop;

@@ -1,12 +1,19 @@
-// pk_pwg_residual_layer_fc: the CTA-pair residual-layer kernel of pwg.cu with FRAME-RATE CONDITIONING (experimental, not
-// the default path; selected by the Python model with PK_PWG_FRAME_COND=1 - DESIGN.md 7.2).
+// pk_pwg_residual_layer_fc: the CTA-pair residual-layer kernel of pwg.cu with FRAME-RATE CONDITIONING (the default
+// residual-stack path of the Python model - DESIGN.md 5).
 //
 // The upsampling network is linear and per channel, so conv1x1_aux(upsample(m'))[t, n] = sum_j U[t, j] (W_aux m')[j, n].
 // GEMM1's two conditioning K-chunks (80 channels of the 1.23 GB sample-rate conditioning tensor, 5 K-steps, 32 KB of
 // resident W_aux) become ONE K-step: A = the tile-relative band table of U (constants of the model,
 // models/_pwg_frame_cond.py), B = the 16-frame window of P = W_aux m' that the tile touches (frame rate, L2 resident).
-// Everything else - pipeline, barriers, gate, residual pass, stores - is the pair kernel of pwg.cu, copied so that the
-// default path stays untouched until this one has been validated on a GPU.
+// Pipeline (round 2, after the phase profile of the round-1 pair kernel showed the tensor pipe waiting ~50 % of the time on
+// its feeders - profiles/r02_pwg_phase_profile.txt):
+//   * 4 smem stages of 32 KB and exactly 4 K-chunks per tile (tap -d, tap +d, conditioning, centre tap): chunk j of every
+//     tile lives in stage j, a stage is refilled one whole tile ahead;
+//   * z never touches shared memory: the gate warps write it (packed bf16x2, hi | lo) with tcgen05.st OVER the GEMM1
+//     accumulator columns they have just read, and GEMM2 takes its A operand from tensor memory.  This removes the z
+//     staging slot from the ring, the generic->async proxy fence and the cluster-scope release on the critical path
+//     (2.4 k cycles per tile), 12 x 4 KB of UMMA smem operand reads per tile, and the acc1_empty barrier: GEMM1 of tile i+2
+//     is issued after GEMM2 of tile i by the same thread, and tcgen05.mma execute in issue order.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,17 +33,21 @@ constexpr int kPwgStoreWarps = 8;
 constexpr int kPwgFirstGateWarp = 4;
 constexpr int kPwgThreads = (kPwgFirstGateWarp + kPwgGateWarps + kPwgStoreWarps) * 32;
 constexpr int kFcG1Chunks = 4;                               // tap -d, tap +d, conditioning, centre tap
-constexpr int kFcStages = 3;
+constexpr int kFcStages = 4;                                 // == kFcG1Chunks: chunk j of every tile uses stage j
 constexpr int kFcStageBytes = 2 * kPwgTile;                  // A hi, A lo
 constexpr int kFcWTile = 64 * kSwizzleBytes;                 // 8 KB: 64 output channels x one K-chunk of one plane
 constexpr int kFcW1Bytes = 3 * 2 * kFcWTile;                 // 48 KB: three tap chunks
 constexpr int kFcW2Bytes = 2 * kFcWTile;                     // 16 KB
 constexpr int kFcPBytes = 2 * kFcWTile;                      // 16 KB: hi | lo of one P window
-constexpr int kFcSmem = kFcStages * kFcStageBytes + kFcW1Bytes + kFcW2Bytes + kFcWTile + 2 * kFcPBytes + 1024 + 256;
+// one P buffer is enough: the window of tile i+1 is loaded into it when stage 2 is handed back, i.e. after the commit that
+// follows the conditioning MMAs of tile i
+constexpr int kFcSmem = kFcStages * kFcStageBytes + kFcW1Bytes + kFcW2Bytes + kFcWTile + kFcPBytes + 1024 + 256;
+static_assert(kFcStages == kFcG1Chunks, "the P buffer / stage reuse argument needs one ring revolution per tile");
+static_assert(kFcSmem <= 227 * 1024, "shared memory budget");
 
 struct FcLayerArgs {
   int batch, t, dil, hop;
-  int u_bmul;                   // 0: one band table for all utterances, 1: one per utterance
+  int u_period, u_start_row, u_end_base;   // compact band table layout (include/parakeet_b200.h)
   int p_row0;                   // first row of this layer's 128 output channels in the P planes
   const int32_t* lens;
   float gate_c[128];
@@ -103,9 +114,8 @@ struct FcTileIter {   // 256-sample tiles of the pair; this CTA owns rows [m0 + 
 
 template <bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwgThreads, 1)
-pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                      const __grid_constant__ CUtensorMap tm_u_hi, const __grid_constant__ CUtensorMap tm_u_lo,
-                    const __grid_constant__ CUtensorMap tm_p_hi, const __grid_constant__ CUtensorMap tm_p_lo,
+pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_u,
+                    const __grid_constant__ CUtensorMap tm_p,          // 4-D maps: both planes of a tile in one TMA box
                       const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                       const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                       const FcLayerArgs p) {
@@ -114,17 +124,15 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
   const uint32_t w1 = smem + kFcStages * kFcStageBytes;        // [chunk][hi | lo] 64-row tiles, resident
   const uint32_t w2 = w1 + kFcW1Bytes;                         // [hi | lo]
   const uint32_t ident = w2 + kFcW2Bytes;                      // this CTA's 64 rows of [0 | I]
-  const uint32_t pbuf = ident + kFcWTile;                      // [2][hi | lo] this CTA's 64 rows of the P window of a tile
-  const uint32_t bars = pbuf + 2 * kFcPBytes;
+  const uint32_t pbuf = ident + kFcWTile;                      // [hi | lo] this CTA's 64 rows of the P window of a tile
+  const uint32_t bars = pbuf + kFcPBytes;
   const uint32_t full_bar = bars;                              // [stages]   (leader's copy is the live one)
   const uint32_t empty_bar = full_bar + 8 * kFcStages;         // [stages]
   const uint32_t acc1_full = empty_bar + 8 * kFcStages;        // [2]
-  const uint32_t acc1_empty = acc1_full + 16;                  // [2] leader
-  const uint32_t acc2_full = acc1_empty + 16;                  // [2]
+  const uint32_t acc2_full = acc1_full + 16;                   // [2]
   const uint32_t acc2_empty = acc2_full + 16;                  // [2] leader
-  const uint32_t z_full = acc2_empty + 16;                     // [2] leader
-  const uint32_t g2_free = z_full + 16;                        // [2]
-  const uint32_t w_bar = g2_free + 16;
+  const uint32_t z_full = acc2_empty + 16;                     // [2] leader: z of tile i is in tensor memory (both CTAs)
+  const uint32_t w_bar = z_full + 16;
   const uint32_t tmem_slot = w_bar + 8;
 
   const int warp = threadIdx.x >> 5;
@@ -135,13 +143,13 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
   (void)kLog2e;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x_hi); tma_prefetch_desc(&tm_x_lo); tma_prefetch_desc(&tm_u_hi); tma_prefetch_desc(&tm_u_lo); tma_prefetch_desc(&tm_p_hi); tma_prefetch_desc(&tm_p_lo);
+    tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_u); tma_prefetch_desc(&tm_p);
     tma_prefetch_desc(&tm_w1_hi); tma_prefetch_desc(&tm_w1_lo); tma_prefetch_desc(&tm_w2_hi); tma_prefetch_desc(&tm_w2_lo);
     for (int s = 0; s < kFcStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init_a(acc1_full + 8 * i, 1); mbar_init_a(acc1_empty + 8 * i, 2 * kPwgGateWarps);
+      mbar_init_a(acc1_full + 8 * i, 1);
       mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, 2 * kPwgStoreWarps);
-      mbar_init_a(z_full + 8 * i, 2 * kPwgGateWarps); mbar_init_a(g2_free + 8 * i, 1);
+      mbar_init_a(z_full + 8 * i, 2 * kPwgGateWarps);
     }
     mbar_init_a(w_bar, 1);
     fence_barrier_init();
@@ -187,10 +195,9 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
       long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       long long tlast = clock64();
       const uint32_t full_leader = mapa_shared(full_bar, 0);
-      int n_g1 = 0;   // tiles whose GEMM1 chunks have been issued (parity selects the P-window buffer)
       auto load_g1 = [&](int b, int m0) {
         for (int j = 0; j < kFcG1Chunks; ++j, ++it) {
-          const int s = it % kFcStages;
+          const int s = j;                                     // kFcStages == kFcG1Chunks
           PK_TICK(1)
           mbar_wait_a(empty_bar + 8 * s, ((it / kFcStages) & 1) ^ 1);
           PK_TICK(0)
@@ -202,45 +209,29 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
             // 64-wide box), B = the same 16 frames of P for this CTA's 64 output channels; frames outside the utterance are
             // out of bounds of the tensor map and read as zero
             if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * (kFcStageBytes + kFcPBytes));
-            tma_load_3d_2sm_a(st, &tm_u_hi, fb, 0, m0, b * p.u_bmul);
-            tma_load_3d_2sm_a(st + kPwgTile, &tm_u_lo, fb, 0, m0, b * p.u_bmul);
+            // band rows of this half tile: first 128 rows of an utterance, the half tiles touching its last 128 rows
+            // (per-utterance block; 2 * 128 clamps halves lying wholly past the end onto the zero block), else interior
+            const int len = p.lens ? min(__ldg(p.lens + b), p.t) : p.t;
+            const int m1 = ((len - 128) >> 7) << 7;
+            const int urow = m0 == 0 ? p.u_start_row
+                             : (m0 + 128 > len - 128) ? p.u_end_base + 384 * b + min(m0 - m1, 256)
+                                                      : m0 % p.u_period;
+            tma_load_4d_2sm_a(st, &tm_u, fb, 0, urow, 0, 0);
             // one K window per PAIR tile (the two CTAs supply the two halves of the same B operand): it starts at the frame of
             // the pair's first row, aligned down to 8 frames (16 B) - TMA faults on an unaligned innermost coordinate
             const int j0 = ((m0 - 128 * static_cast<int>(rank)) / p.hop - 2) & ~7;
-            const uint32_t pb = pbuf + (n_g1 & 1) * kFcPBytes;
-            tma_load_3d_2sm_a(pb, &tm_p_hi, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
-            tma_load_3d_2sm_a(pb + kFcWTile, &tm_p_lo, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b);
+            tma_load_4d_2sm_a(pbuf, &tm_p, fb, j0, p.p_row0 + 64 * static_cast<int>(rank), b, 0);
           } else {
             if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kFcStageBytes);   // the A chunks of both CTAs
             const int wj = j == 0 ? 0 : j == 1 ? 2 : 1;
             const int row = m0 + (wj - 1) * p.dil;
-            tma_load_3d_2sm_a(st, &tm_x_hi, fb, 0, row, b);
-            tma_load_3d_2sm_a(st + kPwgTile, &tm_x_lo, fb, 0, row, b);
+            tma_load_4d_2sm_a(st, &tm_x, fb, 0, row, b, 0);
           }
         }
-        ++n_g1;
-      };
-      int n_g2 = 0;
-      auto load_g2 = [&]() {
-        const int s = it % kFcStages;
-        PK_TICK(1)
-        mbar_wait_a(empty_bar + 8 * s, ((it / kFcStages) & 1) ^ 1);
-        PK_TICK(0)
-        mbar_arrive_a(g2_free + 8 * (n_g2 & 1));   // own gate warps may write z of this tile into the stage
-        ++n_g2;
-        if (leader) mbar_arrive_a(full_bar + 8 * s);   // no TMA in this slot; keeps the stage ring's phases uniform
-        ++it;
       };
       FcTileIter ti(p);
-      int b, m0, nb, nm0;
-      bool have = ti.next(b, m0);
-      if (have) load_g1(b, m0 + 128 * rank);
-      while (have) {
-        const bool have_next = ti.next(nb, nm0);
-        if (have_next) load_g1(nb, nm0 + 128 * rank);
-        load_g2();
-        have = have_next; b = nb; m0 = nm0;
-      }
+      int b, m0;
+      while (ti.next(b, m0)) load_g1(b, m0 + 128 * rank);
       PK_TICK(1)
       if (leader) { PK_TICK_FLUSH(0, 2) }
     }
@@ -262,21 +253,19 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
         }
       };
       auto g1 = [&](int i) {
+        // acc1(i & 1) needs no "empty" barrier: its previous user is tile i-2, whose GEMM2 (the last reader: z lives in the
+        // accumulator's own columns) was issued by this thread before this point, and tcgen05.mma execute in issue order
         const int buf = i & 1;
-        PK_TICK(6)
-        mbar_wait_a(acc1_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
-        PK_TICK(0)
-        tcgen05_fence_after();
         const uint32_t d = tmem_base + buf * 128;
         for (int j = 0; j < kFcG1Chunks; ++j, ++it) {
-          const int s = it % kFcStages;
+          const int s = j;
           PK_TICK(2)
           mbar_wait_a(full_bar + 8 * s, (it / kFcStages) & 1);
           PK_TICK(1)
           tcgen05_fence_after();
           const uint32_t st = smem + s * kFcStageBytes;
           if (j == 2) {
-            mma_chunk(d, st, pbuf + (i & 1) * kFcPBytes, 1, false);     // one K-step: 16 frames of band table x P window
+            mma_chunk(d, st, pbuf, 1, false);                            // one K-step: 16 frames of band table x P window
           } else {
             const int wj = j == 0 ? 0 : j == 1 ? 2 : 1;
             mma_chunk(d, st, w1 + wj * 2 * kFcWTile, 4, j == 0);
@@ -302,17 +291,24 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
       };
       auto g2 = [&](int i) {
         const int buf = i & 1;
-        const int s = it % kFcStages;
         PK_TICK(2)
-        mbar_wait_cluster_a(z_full + 8 * (i & 1), (i >> 1) & 1);   // the gate warps of both CTAs wrote z into stage s
+        mbar_wait_a(z_full + 8 * buf, (i >> 1) & 1);   // the gate warps of both CTAs wrote z over acc1(buf), tcgen05.wait::st done
         PK_TICK(3)
-        mbar_wait_a(full_bar + 8 * s, (it / kFcStages) & 1);
-        PK_TICK(5)
         tcgen05_fence_after();
-        mma_chunk(tmem_base + 256 + buf * 128, smem + s * kFcStageBytes, w2, 4, false);
-        umma_commit_2sm_a(empty_bar + 8 * s);
+        // A from tensor memory: z_hi / z_lo of channels [32 h, 32 h + 32) sit in columns 32 h + [0, 16) / 32 h + [16, 32) of
+        // acc1(buf), one 32-bit column per channel pair, so K-step k (channels 16 k ..) starts at column 32 (k / 2) + 8 (k % 2)
+        const uint32_t za = tmem_base + buf * 128;
+        const uint32_t d2 = tmem_base + 256 + buf * 128;
+        const uint64_t b_hi = make_smem_desc_sw128(w2), b_lo = make_smem_desc_sw128(w2 + kFcWTile);
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+          const uint32_t a_hi = za + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
+          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, 1);           // on top of the residual pass
+          umma_bf16_2sm_ts(d2, a_lo, b_hi + koff, idesc, 1);
+          umma_bf16_2sm_ts(d2, a_hi, b_lo + koff, idesc, 1);
+        }
+        PK_TICK(5)
         umma_commit_2sm_a(acc2_full + 8 * buf);
-        ++it;
       };
       FcTileIter ti(p);
       int b, m0;
@@ -336,38 +332,29 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t acc1_empty_l = mapa_shared(acc1_empty, 0), z_full_l = mapa_shared(z_full, 0);
+    const uint32_t z_full_l = mapa_shared(z_full, 0);
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
     float k_a, k_g;
     asm volatile("mov.f32 %0, %2;\n\tmov.f32 %1, %3;" : "=f"(k_a), "=f"(k_g) : "f"(p.k_a), "f"(p.k_g));
-    uint32_t it = kFcG1Chunks;
     FcTileIter ti(p);
-    int b, m0, nb, nm0;
-    bool have = ti.next(b, m0);
-    for (int i = 0; have; ++i) {
-      const bool have_next = ti.next(nb, nm0);
-      if (have_next) it += kFcG1Chunks;
-      const uint32_t st2 = smem + (it % kFcStages) * kFcStageBytes;
-      ++it;
+    int b, m0;
+    (void)r;
+    for (int i = 0; ti.next(b, m0); ++i) {
       const int buf = i & 1;
       PK_TICK(6)
       mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
       PK_TICK(0)
       tcgen05_fence_after();
-      uint32_t zh[32], zl[32];
+      const uint32_t acc = tmem_base + lane_base + buf * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float va[32], vb[32];
+        uint32_t zw[32];                          // [0, 16): z_hi of channels 32 half + (0 .. 31), [16, 32): z_lo
         __syncwarp();
-        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + half * 32, va);
-        tmem_ld_32x32(tmem_base + lane_base + buf * 128 + 64 + half * 32, vb);
+        tmem_ld_32x32(acc + half * 32, va);
+        tmem_ld_32x32(acc + 64 + half * 32, vb);
         tmem_ld_wait();
-        if (half == 1) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed_a(acc1_empty_l + 8 * buf);
-        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float z[4];
@@ -378,24 +365,18 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_co
             const float t1 = 1.f + e1;
             z[e] = (1.f - e1) * rcp_approx(fmaf(t1, e2, t1));
           }
-          split2(z[0], z[1], zh[half * 16 + j / 2], zl[half * 16 + j / 2]);
-          split2(z[2], z[3], zh[half * 16 + j / 2 + 1], zl[half * 16 + j / 2 + 1]);
+          split2(z[0], z[1], zw[j / 2], zw[16 + j / 2]);
+          split2(z[2], z[3], zw[j / 2 + 1], zw[16 + j / 2 + 1]);
         }
+        // over the a-columns this half has just been read from (the g-columns [64, 128) stay untouched until GEMM1 of tile i+2)
+        tmem_st_32x32(acc + half * 32, zw);
       }
       PK_TICK(1)
-      mbar_wait_a(g2_free + 8 * (i & 1), (i >> 1) & 1);
-      PK_TICK(2)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int chunk = q ^ (r & 7);
-        sts_u4(st2 + r * kSwizzleBytes + chunk * 16, make_uint4(zh[4 * q], zh[4 * q + 1], zh[4 * q + 2], zh[4 * q + 3]));
-        sts_u4(st2 + kPwgTile + r * kSwizzleBytes + chunk * 16, make_uint4(zl[4 * q], zl[4 * q + 1], zl[4 * q + 2], zl[4 * q + 3]));
-      }
-      fence_proxy_async_smem();          // z lives in this CTA's smem and is read by this CTA's tensor core
+      tmem_st_wait();                    // z is in tensor memory
+      tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_a(z_full_l + 8 * (i & 1));
+      if (lane == 0) mbar_arrive_cluster_relaxed_a(z_full_l + 8 * buf);
       PK_TICK(3)
-      have = have_next; b = nb; m0 = nm0;
     }
     PK_TICK(6)
     if (lane == 0 && quarter == 0 && leader) { PK_TICK_FLUSH(16, 7) }
@@ -511,27 +492,25 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   using namespace pk;
   using namespace pk::fc;
   PK_CHECK_ARG(a != nullptr, "args is NULL");
-  PK_CHECK_ARG(a->batch > 0 && a->t > 0 && a->dilation >= 1 && a->hop >= 128, "bad batch/t/dilation/hop (hop must be >= 128)");
+  PK_CHECK_ARG(a->batch > 0 && a->t > 0 && a->dilation >= 1 && a->hop >= 256, "bad batch/t/dilation/hop (hop must be >= 256)");
   PK_CHECK_ARG(a->x_hi && a->x_lo && a->y_hi && a->y_lo && a->u_hi && a->u_lo && a->p_hi && a->p_lo && a->w1_hi && a->w1_lo &&
                a->w2_hi && a->w2_lo && a->bias1 && a->bias2 && a->skip, "NULL pointer in pk_pwg_layer_fc_args");
   PK_CHECK_ARG(a->x_hi != a->y_hi, "layer output must not alias its input");
-  PK_CHECK_ARG(a->u_batches == 1 || a->u_batches == a->batch, "u_batches must be 1 or batch");
+  PK_CHECK_ARG(a->u_period > 0 && (a->u_period % 128) == 0 && a->u_start_row >= a->u_period && a->u_end_base >= a->u_start_row + 128 &&
+               a->u_rows >= a->u_end_base + 384 * a->batch, "bad compact band table layout");
   PK_CHECK_ARG(a->p_rows > 0 && a->p_row0 >= 0 && a->p_row0 + 128 <= a->p_rows && (a->p_ld % 8) == 0 && a->p_ld >= 64 && a->p_frames > 0 &&
                a->p_frames <= a->p_ld, "bad P plane geometry");
   PK_CHECK_ARG(sm_count() >= 2, "needs at least one SM pair");
-  CUtensorMap tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
+  CUtensorMap tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo;
   int rc;
   const uint64_t T = a->t, B = a->batch;
-  if ((rc = encode_tmap_bf16_3d(&tx_hi, a->x_hi, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
-  if ((rc = encode_tmap_bf16_3d(&tx_lo, a->x_lo, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
-  // band table planes (u_batches, T, 64): the K window sits in columns 0..15
-  if ((rc = encode_tmap_bf16_3d(&tu_hi, a->u_hi, 64, T, a->u_batches, 64, T * 64, 128))) return rc;
-  if ((rc = encode_tmap_bf16_3d(&tu_lo, a->u_lo, 64, T, a->u_batches, 64, T * 64, 128))) return rc;
+  if ((rc = encode_tmap_bf16_planes(&tx, a->x_hi, a->x_lo, kPwgR, T, B, kPwgR, T * kPwgR, 128))) return rc;
+  // compact band table planes (u_rows, 64): the K window sits in columns 0..15
+  if ((rc = encode_tmap_bf16_planes(&tu, a->u_hi, a->u_lo, 64, a->u_rows, 1, 64, 0, 128))) return rc;
   // P planes (batch, p_rows, p_ld): frames are the K axis; columns >= p_frames (and < 0) read as zero
   const uint64_t prow = a->p_rows, pld = a->p_ld;
   // (the extent is the padded row length p_ld >= 64: columns [p_frames, p_ld) hold zeros in memory, frames < 0 are out of bounds)
-  if ((rc = encode_tmap_bf16_3d(&tp_hi, a->p_hi, pld, prow, B, pld, prow * pld, 64))) return rc;
-  if ((rc = encode_tmap_bf16_3d(&tp_lo, a->p_lo, pld, prow, B, pld, prow * pld, 64))) return rc;
+  if ((rc = encode_tmap_bf16_planes(&tp, a->p_hi, a->p_lo, pld, prow, B, pld, prow * pld, 64))) return rc;
   const uint64_t k1 = 5 * kChunkK;     // row pitch of the packed W1 (pk_pwg_residual_layer layout); only the 3 tap chunks are read
   if ((rc = encode_tmap_bf16_3d(&tw1_hi, a->w1_hi, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;
   if ((rc = encode_tmap_bf16_3d(&tw1_lo, a->w1_lo, 3 * kChunkK, kPwgG, 1, k1, k1 * kPwgG, 64))) return rc;
@@ -545,7 +524,7 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   }
   FcLayerArgs p;
   p.batch = a->batch; p.t = a->t; p.dil = a->dilation; p.hop = a->hop;
-  p.u_bmul = a->u_batches == 1 ? 0 : 1;
+  p.u_period = a->u_period; p.u_start_row = a->u_start_row; p.u_end_base = a->u_end_base;
   p.p_row0 = a->p_row0;
   p.lens = a->lens; p.skip = a->skip; p.skip_init = a->skip_init;
   constexpr float kLog2e = 1.4426950408889634f;
@@ -561,9 +540,9 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   const int pair_tiles = ((a->t + 255) / 256) * a->batch;
   const int grid = 2 * std::min(pair_tiles, sm_count() / 2);
   if (p.prof != nullptr)
-    pwg_layer_fc_kernel<true><<<grid, kPwgThreads, kFcSmem, st>>>(tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
+    pwg_layer_fc_kernel<true><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
   else
-    pwg_layer_fc_kernel<false><<<grid, kPwgThreads, kFcSmem, st>>>(tx_hi, tx_lo, tu_hi, tu_lo, tp_hi, tp_lo, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
+    pwg_layer_fc_kernel<false><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
   PK_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PK_OK;

@@ -126,3 +126,26 @@ class DistributedBatchSampler:
     def __len__(self):
         full, rem = divmod(self.num_samples, self.batch_size)
         return full if (self.drop_last or rem == 0) else full + 1
+
+
+def synthetic_fastspeech2_batch(seed, lengths, odim=80, idim=80, dur_range=(2, 12)):
+    """LJSpeech-shaped synthetic teacher-forced batch (no dataset is reachable offline): phoneme ids U{1..V-2}, durations
+    U{dur_range}, speech / pitch / energy N(0, 1), zero padded like fastspeech2_single_spk_batch_fn pads - the dict
+    FastSpeech2TrainStep.step takes.  Used by bench.py (cfg 5) and scripts/bench_train.py."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    B, Tmax = len(lengths), max(lengths)
+    text = torch.zeros(B, Tmax, dtype=torch.int64)
+    ds = torch.zeros(B, Tmax, dtype=torch.int64)
+    ps, es = torch.zeros(B, Tmax, 1), torch.zeros(B, Tmax, 1)
+    for b, n in enumerate(lengths):
+        text[b, :n] = torch.randint(1, idim - 1, (n,), generator=g)
+        ds[b, :n] = torch.randint(dur_range[0], dur_range[1] + 1, (n,), generator=g)
+        ps[b, :n] = torch.randn(n, 1, generator=g)
+        es[b, :n] = torch.randn(n, 1, generator=g)
+    olens = ds.sum(1)
+    ys = torch.zeros(B, int(olens.max()), odim)
+    for b in range(B):
+        ys[b, :int(olens[b])] = torch.randn(int(olens[b]), odim, generator=g)
+    return dict(text=text, text_lengths=torch.tensor(lengths, dtype=torch.int64), speech=ys, speech_lengths=olens, durations=ds,
+                pitch=ps, energy=es)

@@ -69,3 +69,60 @@ def tile_band_table(firs, scales, frames, width=8):
     out = torch.zeros(T, KWIN, dtype=torch.float64)
     out.scatter_(1, shift[:, None] + torch.arange(width)[None, :], rows)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Compact tables: what the kernel actually reads (a few MB, L2 resident, independent of batch size and utterance length)
+# ----------------------------------------------------------------------------------------------------------------------
+HALF = 128                     # rows one CTA of the pair loads per tile
+END_ROWS = 3 * HALF            # per-utterance end table: the (up to) two half tiles touching the last EDGE rows + a zero block
+
+
+def period(hop):
+    """Rows after which the interior band table repeats: the tile-relative shift depends on t mod hop, t mod TILE and on
+    (t // hop) mod 8 (the 8-frame alignment of the window start) -> lcm(8 * hop, TILE)."""
+    import math
+    return math.lcm(8 * hop, TILE)
+
+
+def end_tile_start(length):
+    """First row of the first half tile that touches the last EDGE rows of an utterance of `length` samples."""
+    return (length - EDGE) // HALF * HALF
+
+
+def compact_band_tables(firs, scales, frames_list):
+    """-> (table (rows, KWIN) float64, layout dict).  Rows [0, P): interior rows by t mod P (P = period(hop));
+    [P, P + 128): the first half tile of any utterance; then END_ROWS rows per entry of `frames_list` (utterance i): the half
+    tiles starting at end_tile_start(L_i), + HALF, + 2 HALF (rows at or past L_i are zero).  `source_row` below is the
+    kernel's lookup."""
+    hop = 1
+    for s_ in scales:
+        hop *= s_
+    P = period(hop)
+    big = tile_band_table(firs, scales, 2 * (P // hop) + 8)          # long enough for one whole interior period
+    assert big.shape[0] >= 2 * P + EDGE
+    parts = [big[P:2 * P], big[:HALF]]
+    cache = {}
+    for nf in frames_list:
+        nf = int(nf)
+        if nf not in cache:
+            L = nf * hop
+            m1 = end_tile_start(L)
+            full = tile_band_table(firs, scales, nf) if nf > 0 else torch.zeros(0, KWIN, dtype=torch.float64)
+            blk = torch.zeros(END_ROWS, KWIN, dtype=torch.float64)
+            if nf > 0:
+                n = min(END_ROWS, L - m1)
+                blk[:n] = full[m1:m1 + n]
+            cache[nf] = blk
+        parts.append(cache[nf])
+    return torch.cat(parts), dict(period=P, start_row=P, end_base=P + HALF, hop=hop)
+
+
+def source_row(m, length, b, layout):
+    """Row of the compact table holding the band rows of the half tile [m, m + 128) of utterance b (length samples):
+    mirrors the producer of pwg_layer_fc_kernel."""
+    if m == 0:
+        return layout["start_row"]
+    if m + HALF > length - EDGE:
+        return layout["end_base"] + END_ROWS * b + min(m - end_tile_start(length), 2 * HALF)
+    return m % layout["period"]

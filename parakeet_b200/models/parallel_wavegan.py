@@ -191,11 +191,17 @@ class PWGGenerator(Layer):
             self._ws.clear()
             dev = self.device
             ws = dict(xa=Split.zeros((B, T, 64), dev), xb=Split.zeros((B, T, 64), dev),
-                      c=Split.empty((B, T, self.aux_channels), dev),
+                      c=Split.empty((B, T, self.aux_channels), dev) if not self._frame_cond() else None,   # sample-rate planes: legacy path only
                       skip=torch.empty(B, T, 64, dtype=torch.float32, device=dev),
                       conv_in=torch.empty(B, T // self.upsample_factor, self.aux_channels, dtype=torch.float32, device=dev))
             self._ws[key] = ws
         return ws
+
+    @staticmethod
+    def _frame_cond():
+        """Frame-rate conditioning (csrc/pwg_fc.cu) is the default; PK_PWG_FRAME_COND=0 selects the round-1 kernel that
+        streams the sample-rate conditioning planes (kept for A/B measurements)."""
+        return os.environ.get("PK_PWG_FRAME_COND", "1") != "0"
 
     # -- forward (reference :445-472) ------------------------------------------------------------------------------
     def forward(self, x, c, lens=None):
@@ -211,6 +217,9 @@ class PWGGenerator(Layer):
         B, _, T = x.shape
         frames = c.shape[-1] - 2 * self.aux_context_window
         assert frames * self.upsample_factor == T, (c.shape, x.shape)   # reference :462
+        fcond = self._frame_cond()
+        if self._ws and (next(iter(self._ws.values()))["c"] is None) != fcond:
+            self._ws.clear()                                         # the toggle changed between calls
         ws = self._workspace(B, T)
         st = _stream()
         x = x.contiguous().float()
@@ -223,14 +232,15 @@ class PWGGenerator(Layer):
         _lib.check(L.pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]), pk["fir_host"].ctypes.data_as(C.c_void_p),
                                      pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
                                      self.aux_channels, frames, self.aux_context_window, _ptr(frame_lens), _ptr(ws["conv_in"]),
-                                     None, _ptr(ws["c"].hi), _ptr(ws["c"].lo), st), "pk_pwg_upsample")
+                                     None, _ptr(ws["c"].hi) if not fcond else None, _ptr(ws["c"].lo) if not fcond else None, st),
+                   "pk_pwg_upsample")
         _lib.check(L.pk_pwg_first_conv(_ptr(x), _ptr(pk["first_w"]), _ptr(pk["first_b"]), lens_p, B, T, _ptr(ws["xa"].hi),
                                        _ptr(ws["xa"].lo), st), "pk_pwg_first_conv")
         if lens is not None:
             ws["xb"].hi.zero_()
             ws["xb"].lo.zero_()
         src, dst = ws["xa"], ws["xb"]
-        if os.environ.get("PK_PWG_FRAME_COND", "0") == "1":
+        if fcond:
             return self._forward_frame_cond(pk, ws, src, dst, B, T, frames, lens, frame_lens, st)
         args = PwgLayerArgs()
         args.batch, args.t, args.aux_channels = B, T, self.aux_channels
@@ -261,15 +271,15 @@ class PWGGenerator(Layer):
         return out
 
     def _forward_frame_cond(self, pk, ws, src, dst, B, T, frames, lens, frame_lens, st):
-        """EXPERIMENTAL residual stack with frame-rate conditioning (csrc/pwg_fc.cu): conv1x1_aux is applied to
-        conv_in(mel) at frame rate (P), and each layer multiplies the tile-relative band table of the upsampling operator
-        with the 16-frame window of P it touches.  Not validated on a GPU yet - never the default."""
+        """Residual stack with frame-rate conditioning (csrc/pwg_fc.cu): conv1x1_aux of all 30 layers is applied
+        to conv_in(mel) at frame rate by ONE GEMM per forward (P), and each layer multiplies the band table of the (linear,
+        per-channel) upsampling operator with the 16-frame window of P its tile touches - no sample-rate conditioning tensor."""
         from . import _pwg_frame_cond as fc
         L = _lib.lib()
         hop, A, NL = self.upsample_factor, self.aux_channels, self.layers
         if "aux_all" not in pk:
             # the 30 aux weights stacked as the row operand of one GEMM per forward, P[b] = W_aux_all (30*128 x aux) . m'[b]^T,
-            # and the FIRs of the upsampling stages for the band tables (packed lazily: the default path never needs them)
+            # and the FIRs of the upsampling stages for the band tables
             fp = {k: v.detach().float().cpu() for k, v in self._folded().items()}
             aux_all = torch.cat([fp[f"conv_layers.{i}.conv1x1_aux.weight"][:, :, 0] for i in range(NL)], dim=0)
             pk["aux_all"] = Split.from_f32(aux_all.contiguous().to(self.device).unsqueeze(0))      # (1, 30*128, aux)
@@ -278,51 +288,59 @@ class PWGGenerator(Layer):
                 firs.append(torch.from_numpy(pk["fir_host"][off:off + 2 * s_ + 1].copy()))
                 off += 2 * s_ + 1
             pk["firs"] = firs
+            pk["band_tables"] = {}
         m1 = ws["conv_in"]                                               # (B, frames, aux) written by pk_pwg_upsample above
         if frame_lens is not None:
             ops.mask_rows_(m1, frame_lens)                               # frames past an utterance's end contribute nothing
         m1s = Split.from_f32(m1)
         Fp = max((frames + 7) // 8 * 8, 64)
-        P = Split.zeros((B, NL * 128, Fp), self.device)
+        key = ("P", B, Fp)
+        P = ws.get(key)
+        if P is None:
+            P = ws[key] = Split.zeros((B, NL * 128, Fp), self.device)    # columns [frames, Fp) stay zero
         a_spec = dict(rows=NL * 128, cols=A, ld=A, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
         b_spec = dict(rows=frames, cols=A, ld=A, batch_stride=frames * A, batches=B, bmul=1, hmul=0, col0=0, colh=0)
         ops.batched_matmul_nt(pk["aux_all"], m1s, batch=B, heads=1, m=NL * 128, n=frames, k=A, a_spec=a_spec, b_spec=b_spec,
                               y_split=P, y_batch_stride=NL * 128 * Fp, y_head_stride=0, y_ld=Fp)
-        # band tables: one per distinct utterance length (constants of the model), shared when the batch is not ragged
-        cache = self.__dict__.setdefault("_band_tables", {})
-
-        def table(nf):
-            if nf not in cache:
-                tb = torch.zeros(nf * hop, 64, dtype=torch.float32)
-                tb[:, :fc.KWIN] = fc.tile_band_table(pk["firs"], self.upsample_scales, nf).float()
-                cache[nf] = tb
-            return cache[nf]
+        # compact band table (constants of the model + the utterance lengths of this batch; a few MB, cached per length tuple)
         if frame_lens is None:
-            U = Split.from_f32(table(frames).to(self.device).unsqueeze(0))
-            u_batches = 1
+            lens_key = (frames,) * B
         else:
-            full = torch.zeros(B, T, 64, dtype=torch.float32)
-            for i, nf in enumerate(frame_lens.cpu().tolist()):
-                if nf > 0:
-                    full[i, :nf * hop] = table(int(nf))
-            U = Split.from_f32(full.to(self.device))
-            u_batches = B
+            lens_key = tuple(int(v) for v in frame_lens.cpu().tolist())   # host sync: ragged batches only (lengths are host data
+                                                                           # in the reference's callers too, synthesize.py:96-104)
+        ent = pk["band_tables"].get(lens_key)
+        if ent is None:
+            if len(pk["band_tables"]) >= 16:
+                pk["band_tables"].pop(next(iter(pk["band_tables"])))
+            tab, lay = fc.compact_band_tables(pk["firs"], self.upsample_scales, lens_key)
+            wide = torch.zeros(tab.shape[0], 64, dtype=torch.float32)
+            wide[:, :fc.KWIN] = tab.float()
+            ent = pk["band_tables"][lens_key] = (Split.from_f32(wide.to(self.device)), lay)
+        U, lay = ent
         args = _lib.PwgLayerFcArgs()
         args.batch, args.t, args.hop = B, T, hop
         args.lens = lens.data_ptr() if lens is not None else None
-        args.u_hi, args.u_lo, args.u_batches = U.hi.data_ptr(), U.lo.data_ptr(), u_batches
+        args.u_hi, args.u_lo, args.u_rows = U.hi.data_ptr(), U.lo.data_ptr(), U.hi.shape[0]
+        args.u_period, args.u_start_row, args.u_end_base = lay["period"], lay["start_row"], lay["end_base"]
         args.p_hi, args.p_lo, args.p_rows, args.p_ld, args.p_frames = P.hi.data_ptr(), P.lo.data_ptr(), NL * 128, Fp, frames
         args.skip = ws["skip"].data_ptr()
         args.prof = self._prof.data_ptr() if getattr(self, "_prof", None) is not None else None
-        for i, lay in enumerate(pk["layers"]):
-            args.dilation, args.p_row0 = lay["dil"], i * 128
+        ev = getattr(self, "_layer_events", None)
+        if ev is not None:   # bench.py: CUDA events around the 30 residual-layer launches, on the launching stream
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_a.record()
+        for i, lay_ in enumerate(pk["layers"]):
+            args.dilation, args.p_row0 = lay_["dil"], i * 128
             args.x_hi, args.x_lo, args.y_hi, args.y_lo = src.hi.data_ptr(), src.lo.data_ptr(), dst.hi.data_ptr(), dst.lo.data_ptr()
-            args.w1_hi, args.w1_lo = lay["w1"].hi.data_ptr(), lay["w1"].lo.data_ptr()
-            args.w2_hi, args.w2_lo = lay["w2"].hi.data_ptr(), lay["w2"].lo.data_ptr()
-            args.bias1, args.bias2 = lay["b1"].ctypes.data, lay["b2"].ctypes.data
+            args.w1_hi, args.w1_lo = lay_["w1"].hi.data_ptr(), lay_["w1"].lo.data_ptr()
+            args.w2_hi, args.w2_lo = lay_["w2"].hi.data_ptr(), lay_["w2"].lo.data_ptr()
+            args.bias1, args.bias2 = lay_["b1"].ctypes.data, lay_["b2"].ctypes.data
             args.skip_init = 1 if i == 0 else 0
             _lib.check(L.pk_pwg_residual_layer_fc(C.byref(args), st), "pk_pwg_residual_layer_fc")
             src, dst = dst, src
+        if ev is not None:
+            ev_b.record()
+            ev.append((ev_a, ev_b))
         out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
         _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")

@@ -37,15 +37,17 @@ class Split:
     def shape(self):
         return self.hi.shape
 
+    # Both planes come from ONE allocation, lo right after hi: kernels that stream a tile of both planes can then fetch them
+    # with a single 4-D TMA box (the plane is the outermost dimension; csrc/pwg_fc.cu) instead of two loads.
     @staticmethod
     def empty(shape, device):
-        return Split(torch.empty(shape, dtype=torch.bfloat16, device=device),
-                     torch.empty(shape, dtype=torch.bfloat16, device=device))
+        buf = torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
+        return Split(buf[0], buf[1])
 
     @staticmethod
     def zeros(shape, device):
-        return Split(torch.zeros(shape, dtype=torch.bfloat16, device=device),
-                     torch.zeros(shape, dtype=torch.bfloat16, device=device))
+        buf = torch.zeros((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
+        return Split(buf[0], buf[1])
 
     @staticmethod
     def from_f32(x):

@@ -288,6 +288,38 @@ def test_pwg_frame_rate_conditioning_tables_reproduce_the_aux_path():
         assert worst < 1e-12 * max(1.0, float(ref.abs().max())), (frames, worst)
 
 
+def test_pwg_compact_band_tables_equal_the_per_length_tables():
+    """The kernel reads a compact table (one interior period + start block + 384 end rows per utterance, indexed by
+    _pwg_frame_cond.source_row): every half tile of utterances of several lengths must equal the per-length table above."""
+    from oracle import pwg as opwg
+    from parakeet_b200.models import _pwg_frame_cond as fc
+    cfg = opwg.DEFAULT_GENERATOR_PARAMS
+    scales = cfg["upsample_scales"]
+    params = {k: v.double() for k, v in opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True)).items()}
+    firs = [params[f"upsample_net.upsample.up_layers.{2 * i + 1}.weight"].reshape(-1) for i in range(len(scales))]
+    frames_list = [1, 2, 3, 7, 9, 40, 64, 65, 129, 400]
+    table, lay = fc.compact_band_tables(firs, scales, frames_list)
+    assert lay["period"] == 19200 and table.shape[0] == 19200 + 128 + 384 * len(frames_list)
+    for b, nf in enumerate(frames_list):
+        L = nf * lay["hop"]
+        full = fc.tile_band_table(firs, scales, nf)
+        for m in range(0, (L + 255) // 256 * 256, 128):                 # every half tile of every pair tile with a valid row
+            r = fc.source_row(m, L, b, lay)
+            got = table[r:r + 128].clone()
+            want = torch.zeros(128, fc.KWIN, dtype=torch.float64)
+            n = max(0, min(128, L - m))
+            want[:n] = full[m:m + n]
+            # entry k of a row multiplies frame window_start(pair tile) + k of P; frames outside [0, nf) read as zero (TMA
+            # bounds / zero padding), so coefficients for them are "don't care" (short utterances keep them at zero, the
+            # interior period carries the coefficient a longer utterance would use)
+            j = fc.window_start(m // fc.TILE * fc.TILE, lay["hop"]) + torch.arange(fc.KWIN)
+            live = ((j >= 0) & (j < nf)).to(torch.float64)
+            got, want = got * live, want * live
+            assert torch.equal(got[:n], want[:n]), (nf, m)
+            if m + 128 > L - fc.EDGE:                                    # end blocks are zero past the utterance
+                assert got[n:].abs().max() == 0 if n < 128 else True
+
+
 def test_length_regulator_against_vectors_produced_by_the_reference_code():
     """tests/golden/ref_executed.npz: outputs of the reference's own LengthRegulator.forward (its numpy expansion-matrix loop,
     length_regulator.py:46-89) executed by scripts/make_golden_ref.py behind a ten-line torch stand-in for the four paddle
