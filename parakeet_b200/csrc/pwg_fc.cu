@@ -261,7 +261,11 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
           const int s = j;
           PK_TICK(2)
           mbar_wait_a(full_bar + 8 * s, (it / kFcStages) & 1);
-          PK_TICK(1)
+          if (kProf) {                       // wait-for-data time per chunk: buckets 0 (tap -d), 1 (tap +d), 6 (conditioning), 7 (centre)
+            const long long n_ = clock64();
+            tacc[j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 6 : 7] += n_ - tlast;
+            tlast = n_;
+          }
           tcgen05_fence_after();
           const uint32_t st = smem + s * kFcStageBytes;
           if (j == 2) {
