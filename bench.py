@@ -262,8 +262,11 @@ def cfg5_train_step(dev, rank, world, steps, barrier, max_over_ranks):
     from parakeet_b200.training import FastSpeech2TrainStep
     GLOBAL = 64
     per = GLOBAL // world
-    m = ljspeech_fastspeech2(dev, stop_gradient_from_pitch_predictor=True)      # same seed -> same weights on every rank
-    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    yaml_rates = dict(transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2, transformer_enc_attn_dropout_rate=0.2,
+                      transformer_dec_dropout_rate=0.2, transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2,
+                      pitch_predictor_dropout=0.5, energy_predictor_dropout=0.5, pitch_embed_dropout=0.0, energy_embed_dropout=0.0)
+    m = ljspeech_fastspeech2(dev, stop_gradient_from_pitch_predictor=True, **yaml_rates)   # same seed -> same weights on every rank
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=True, seed=1000 + rank)       # conf/default.yaml:56-74 dropout rates
     g = torch.Generator().manual_seed(5)
     lengths = torch.randint(60, 141, (GLOBAL,), generator=g).tolist()
     batch = synth_train_batch(55, lengths[rank * per:(rank + 1) * per])
@@ -296,7 +299,7 @@ def cfg5_train_step(dev, rank, world, steps, barrier, max_over_ranks):
         bus = 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9
     if rank != 0:
         return None
-    return {"workload": "fastspeech2 training step, global batch 64 (T ~ U{60..140} phonemes, durations U{2..12})", "scaling": "strong",
+    return {"workload": "fastspeech2 training step with the yaml's dropout rates, global batch 64 (T ~ U{60..140} phonemes, durations U{2..12})", "scaling": "strong",
             "n_gpus": world, "per_gpu_batch": per, "ms_per_step": ms, "steps_per_s": 1e3 / ms,
             "mel_frames_per_s": float(frames_local.item()) / (ms * 1e-3), "loss": [float(v) for v in losses],
             "grad_allreduce_bytes": nbytes, "allreduce_ms": ar_ms, "allreduce_bus_gbs": bus,

@@ -383,6 +383,14 @@ int pk_scalar_conv_wgrad(const float* dhs, const float* track, int32_t batch, in
                          pk_stream_t stream);
 /* paddle.optimizer.Adam step on a flat buffer (training/optimizer.py:17-46): g * grad_scale (1/world for DataParallel),
  * lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), p -= lr_t * m / (sqrt(v) + eps * sqrt(1 - beta2^t)). */
+/* nn.Dropout in training mode (upscale_in_train): y[i] = keep(i) ? x[i] / (1 - p) : 0, keep(i) = word (i & 3) of
+ * Philox4x32-10(counter {i >> 2 low, high, site, step}, key {seed low, high}) >= p * 2^32.  Input fp32 x or split planes
+ * (x_hi + x_lo), outputs fp32 and/or split planes; in place allowed.  The backward pass applies the same call to the gradient
+ * (same seed / site / step regenerate the mask).  Reference: the Dropout layers of parakeet/modules/fastspeech2_transformer/
+ * {embedding.py:79,126, attention.py:124, encoder_layer.py:101,108, multi_layer_conv.py:76}, fastspeech2_predictor/
+ * {duration_predictor.py:82, variance_predictor.py:73}, tacotron2/decoder.py:144-180 (Postnet). */
+int pk_dropout(const float* x, const void* x_hi, const void* x_lo, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step,
+               float* y, void* y_hi, void* y_lo, pk_stream_t stream);
 int pk_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
             int32_t step, float grad_scale, pk_stream_t stream);
 

@@ -39,6 +39,72 @@ LJSPEECH_MODEL_CFG = dict(  # examples/fastspeech2/ljspeech/conf/default.yaml:33
 )
 
 
+# ----------------------------------------------------------------------------------------
+# Dropout (paddle.nn.Dropout, upscale_in_train).  The reference draws its masks from Paddle's generator, which cannot be
+# reproduced; what CAN be checked is the arithmetic around a GIVEN mask.  The CUDA path derives its masks from
+# Philox4x32-10 keyed by (seed, step, site, element index) - include/parakeet_b200.h: pk_dropout - and this class restates
+# that generator in numpy so that the oracle applies the very same masks at the reference's dropout sites.
+# ----------------------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (Salmon et al. 2011): uint32 arrays (or scalars) -> four uint32 arrays."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(v, dtype=np.uint64) & 0xFFFFFFFF for v in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(M0) * c0, np.uint64(M1) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & mask, lo1, (hi0 ^ c3 ^ k1) & mask, lo0
+        k0, k1 = (k0 + np.uint64(W0)) & mask, (k1 + np.uint64(W1)) & mask
+    return c0, c1, c2, c3
+
+
+def dropout_site(stack, layer, kind):
+    """Site numbering shared with parakeet_b200/training/fs2_step.py.  stack: 0 encoder, 1 decoder, 2 pitch, 3 energy,
+    4 duration predictor, 5 postnet; kind: 0 positional encoding, 1 attention probabilities, 2 attention sub-layer output,
+    3 feed-forward hidden, 4 feed-forward sub-layer output, 5 predictor layer, 6 postnet layer."""
+    return stack * 1000 + layer * 10 + kind
+
+
+class PhiloxDropout:
+    """drop(site, x, p) with x laid out exactly as the CUDA path lays the tensor out (the element index is the linear index of
+    that contiguous tensor)."""
+
+    def __init__(self, seed, step):
+        self.seed, self.step = int(seed), int(step)
+
+    def keep_mask(self, site, n, p):
+        blocks = (n + 3) // 4
+        idx = np.arange(blocks, dtype=np.uint64)
+        w = philox4x32_10(idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.full(blocks, site, dtype=np.uint64),
+                          np.full(blocks, self.step, dtype=np.uint64), self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF)
+        r = np.stack(w, axis=1).reshape(-1)[:n]
+        t = p * 4294967296.0
+        thresh = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+        return torch.from_numpy((r >= np.uint64(thresh)).astype(np.float32))
+
+    def __call__(self, site, x, p):
+        if p <= 0:
+            return x
+        keep = self.keep_mask(site, x.numel(), p).reshape(x.shape)
+        return x * keep * np.float32(1.0 / (1.0 - np.float32(p)))
+
+
+def _drop(dropout, site, x, p):
+    return x if dropout is None else dropout(site, x, p)
+
+
+# the reference's constructor defaults (fastspeech2.py:85-113); the shipped yamls set 0.2 for the six transformer rates, 0.5 for the
+# pitch / energy predictors and 0.0 for the two embed dropouts (examples/fastspeech2/*/conf/default.yaml:56-74)
+DROPOUT_DEFAULTS = dict(transformer_enc_dropout_rate=0.1, transformer_enc_positional_dropout_rate=0.1, transformer_enc_attn_dropout_rate=0.1,
+                        transformer_dec_dropout_rate=0.1, transformer_dec_positional_dropout_rate=0.1, transformer_dec_attn_dropout_rate=0.1,
+                        duration_predictor_dropout_rate=0.1, pitch_predictor_dropout=0.5, energy_predictor_dropout=0.5,
+                        postnet_dropout_rate=0.5, pitch_embed_dropout=0.5, energy_embed_dropout=0.5)
+YAML_DROPOUT = dict(DROPOUT_DEFAULTS, transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2,
+                    transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2, transformer_dec_positional_dropout_rate=0.2,
+                    transformer_dec_attn_dropout_rate=0.2, pitch_embed_dropout=0.0, energy_embed_dropout=0.0)
+
+
 def paddle_round(x):
     """paddle.round: half away from zero (C round), unlike torch.round (half to even)."""
     return torch.sign(x) * torch.floor(torch.abs(x) + 0.5)
@@ -79,8 +145,9 @@ def layer_norm(p, name, x):
     return F.layer_norm(x, (x.shape[-1],), p[name + ".weight"], p[name + ".bias"], eps=1e-5)
 
 
-def attention(p, pre, x, mask, n_head):
-    """MultiHeadedAttention.forward (attention.py:133-156); query = key = value = x; mask (B,1,T) bool or None."""
+def attention(p, pre, x, mask, n_head, dropout=None, site=0, rate=0.0):
+    """MultiHeadedAttention.forward (attention.py:133-156); query = key = value = x; mask (B,1,T) bool or None.
+    Dropout on the attention probabilities (:124) is indexed in the CUDA layout (B*H, T, ceil64(T))."""
     B, T, A = x.shape
     dk = A // n_head
     q = linear(p, pre + "linear_q", x).reshape(B, T, n_head, dk).transpose(1, 2)
@@ -93,6 +160,10 @@ def attention(p, pre, x, mask, n_head):
         attn = masked_fill(torch.softmax(scores, dim=-1), m, 0.0)
     else:
         attn = torch.softmax(scores, dim=-1)
+    if dropout is not None and rate > 0:
+        Tp = (T + 63) // 64 * 64
+        padded = F.pad(attn, (0, Tp - T)).reshape(B * n_head, T, Tp)
+        attn = dropout(site, padded, rate).reshape(B, n_head, T, Tp)[..., :T]
     ctx = torch.matmul(attn, v).transpose(1, 2).reshape(B, T, A)
     return linear(p, pre + "linear_out", ctx)
 
@@ -104,20 +175,25 @@ def conv1d_cl(p, name, x, bias=True):
     return F.conv1d(x.transpose(1, 2), w, p[name + ".bias"] if bias else None, padding=(k - 1) // 2).transpose(1, 2)
 
 
-def multi_layered_conv1d(p, pre, x):
-    """multi_layer_conv.py:62-77."""
-    return conv1d_cl(p, pre + "w_2", torch.relu(conv1d_cl(p, pre + "w_1", x)))
+def multi_layered_conv1d(p, pre, x, dropout=None, site=0, rate=0.0):
+    """multi_layer_conv.py:62-77 (dropout between relu(w_1) and w_2, :76)."""
+    return conv1d_cl(p, pre + "w_2", _drop(dropout, site, torch.relu(conv1d_cl(p, pre + "w_1", x)), rate))
 
 
-def encoder_layer(p, pre, x, mask, n_head):
-    """EncoderLayer.forward (encoder_layer.py:64-115), pre-LN, concat_after=False, cache=None."""
-    x = x + attention(p, pre + "self_attn.", layer_norm(p, pre + "norm1", x), mask, n_head)
-    x = x + multi_layered_conv1d(p, pre + "feed_forward.", layer_norm(p, pre + "norm2", x))
+def encoder_layer(p, pre, x, mask, n_head, dropout=None, stack=0, layer=0, rates=(0.0, 0.0)):
+    """EncoderLayer.forward (encoder_layer.py:64-115), pre-LN, concat_after=False, cache=None.  rates = (dropout_rate of the
+    layer: both sub-layer outputs :101,108 and the feed-forward hidden, attention_dropout_rate)."""
+    r_layer, r_attn = rates
+    a = attention(p, pre + "self_attn.", layer_norm(p, pre + "norm1", x), mask, n_head, dropout, dropout_site(stack, layer, 1), r_attn)
+    x = x + _drop(dropout, dropout_site(stack, layer, 2), a, r_layer)
+    f = multi_layered_conv1d(p, pre + "feed_forward.", layer_norm(p, pre + "norm2", x), dropout, dropout_site(stack, layer, 3), r_layer)
+    x = x + _drop(dropout, dropout_site(stack, layer, 4), f, r_layer)
     return x
 
 
-def encoder(p, pre, xs, masks, n_layers, n_head, embed=True):
-    """Encoder.forward (encoder.py:171-192).  embed=True: Embedding(padding_idx=0)+ScaledPE; False: ScaledPE only."""
+def encoder(p, pre, xs, masks, n_layers, n_head, embed=True, dropout=None, stack=0, rates=(0.0, 0.0, 0.0)):
+    """Encoder.forward (encoder.py:171-192).  embed=True: Embedding(padding_idx=0)+ScaledPE; False: ScaledPE only.
+    rates = (dropout_rate, positional_dropout_rate, attention_dropout_rate) as the reference's constructor names them."""
     if embed:
         w = p[pre + "embed.0.weight"]
         e = w[xs]
@@ -127,30 +203,32 @@ def encoder(p, pre, xs, masks, n_layers, n_head, embed=True):
     else:
         alpha = p[pre + "embed.0.alpha"]
     xs = xs + alpha * positional_encoding(xs.shape[1], xs.shape[2])  # ScaledPositionalEncoding.forward :111-126
+    xs = _drop(dropout, dropout_site(stack, 0, 0), xs, rates[1])      # :126
     for i in range(n_layers):
-        xs = encoder_layer(p, f"{pre}encoders.{i}.", xs, masks, n_head)
+        xs = encoder_layer(p, f"{pre}encoders.{i}.", xs, masks, n_head, dropout, stack, i, (rates[0], rates[2]))
     return layer_norm(p, pre + "after_norm", xs)
 
 
-def predictor_stack(p, pre, xs, n_layers):
+def predictor_stack(p, pre, xs, n_layers, dropout=None, stack=0, rate=0.0):
     """[Conv1D -> ReLU -> LayerNorm(channel) -> Dropout] x n (duration_predictor.py:69-83, variance_predictor.py:59-76)."""
     for i in range(n_layers):
         xs = torch.relu(conv1d_cl(p, f"{pre}conv.{i}.0", xs))
         xs = layer_norm(p, f"{pre}conv.{i}.2", xs)  # LayerNorm(n_chans, dim=1) == LN over channels in (B,T,C) view
+        xs = _drop(dropout, dropout_site(stack, i, 5), xs, rate)
     return xs
 
 
-def variance_predictor(p, pre, xs, x_masks, n_layers):
+def variance_predictor(p, pre, xs, x_masks, n_layers, dropout=None, stack=0, rate=0.0):
     """VariancePredictor.forward (variance_predictor.py:77-104); x_masks (B,T,1) True on padding."""
-    xs = linear(p, pre + "linear", predictor_stack(p, pre, xs, n_layers))
+    xs = linear(p, pre + "linear", predictor_stack(p, pre, xs, n_layers, dropout, stack, rate))
     if x_masks is not None:
         xs = masked_fill(xs, x_masks, 0.0)
     return xs
 
 
-def duration_predictor(p, pre, xs, x_masks, n_layers, is_inference, offset=1.0):
+def duration_predictor(p, pre, xs, x_masks, n_layers, is_inference, offset=1.0, dropout=None, rate=0.0):
     """DurationPredictor._forward (duration_predictor.py:85-103)."""
-    xs = linear(p, pre + "linear", predictor_stack(p, pre, xs, n_layers)).squeeze(-1)
+    xs = linear(p, pre + "linear", predictor_stack(p, pre, xs, n_layers, dropout, 4, rate)).squeeze(-1)
     if is_inference:
         xs = torch.clip(paddle_round(torch.exp(xs) - offset), min=0)
     if x_masks is not None:
@@ -184,7 +262,7 @@ def length_regulator(xs, ds, alpha=1.0):
     return length_regulator_expand(xs, ds.to(torch.int64))
 
 
-def postnet(p, xs, n_layers, train_bn=False, new_stats=None):
+def postnet(p, xs, n_layers, train_bn=False, new_stats=None, dropout=None, rate=0.0):
     """Postnet.forward (tacotron2/decoder.py:182-198) on (B, odim, T); dropout identity.  BatchNorm1D in eval mode uses the
     running statistics; with train_bn=True (model.train()) it uses the batch statistics (biased variance) and the updated
     running statistics (paddle momentum 0.9: running = 0.9 * running + 0.1 * batch, biased variance) go to `new_stats`."""
@@ -202,6 +280,8 @@ def postnet(p, xs, n_layers, train_bn=False, new_stats=None):
                 + p[pre + "bias"][None, :, None]
             if i != n_layers - 1:
                 xs = torch.tanh(xs)
+            if dropout is not None and rate > 0:       # decoder.py:144-180: Dropout closes every postnet layer; CUDA layout (B, T, C)
+                xs = dropout(dropout_site(5, i, 6), xs.transpose(1, 2).contiguous(), rate).transpose(1, 2)
             continue
         xs = F.batch_norm(xs, p[pre + "_mean"], p[pre + "_variance"], p[pre + "weight"], p[pre + "bias"], False, 0.0, 1e-5)
         if i != n_layers - 1:
@@ -211,8 +291,9 @@ def postnet(p, xs, n_layers, train_bn=False, new_stats=None):
 
 def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0,
                 return_intermediates=False, train_bn=False, new_stats=None, stop_gradient_from_pitch_predictor=False,
-                stop_gradient_from_energy_predictor=False):
+                stop_gradient_from_energy_predictor=False, dropout=None, rates=None):
     """FastSpeech2._forward (fastspeech2.py:377-466), single speaker, no tones.
+    dropout: None (eval / p = 0) or a PhiloxDropout; rates: dict with the reference's constructor keywords (DROPOUT_DEFAULTS).
 
     xs (B,Tmax) int64; ilens (B,); training: olens (B,), ds (B,Tmax) int64, ps/es (B,Tmax,1).
     Returns before_outs, after_outs, d_outs, p_outs, e_outs.
@@ -220,13 +301,15 @@ def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inf
     cfg = {**LJSPEECH_MODEL_CFG, **(cfg or {})}
     nh = cfg["aheads"]
     x_masks = make_non_pad_mask(ilens, xs.shape[1]).unsqueeze(-2)          # _source_mask :618-641
-    hs = encoder(p, "encoder.", xs, x_masks, cfg["elayers"], nh, embed=True)
+    R = {**DROPOUT_DEFAULTS, **(rates or {})}
+    hs = encoder(p, "encoder.", xs, x_masks, cfg["elayers"], nh, embed=True, dropout=dropout, stack=0,
+                 rates=(R["transformer_enc_dropout_rate"], R["transformer_enc_positional_dropout_rate"], R["transformer_enc_attn_dropout_rate"]))
     d_masks = make_pad_mask(ilens, xs.shape[1])
     # fastspeech2.py:412-419 (stop_gradient_from_*_predictor -> hs.detach())
     p_outs = variance_predictor(p, "pitch_predictor.", hs.detach() if stop_gradient_from_pitch_predictor else hs,
-                                d_masks.unsqueeze(-1), cfg["pitch_predictor_layers"])
+                                d_masks.unsqueeze(-1), cfg["pitch_predictor_layers"], dropout, 2, R["pitch_predictor_dropout"])
     e_outs = variance_predictor(p, "energy_predictor.", hs.detach() if stop_gradient_from_energy_predictor else hs,
-                                d_masks.unsqueeze(-1), cfg["energy_predictor_layers"])
+                                d_masks.unsqueeze(-1), cfg["energy_predictor_layers"], dropout, 3, R["energy_predictor_dropout"])
     if is_inference:
         d_outs = duration_predictor(p, "duration_predictor.", hs, d_masks, cfg["duration_predictor_layers"], True)
         p_embs = conv1d_cl(p, "pitch_embed.0", p_outs)
@@ -234,21 +317,24 @@ def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inf
         hs = hs + e_embs + p_embs
         hs_lr = length_regulator(hs, d_outs, alpha)
     else:
-        d_outs = duration_predictor(p, "duration_predictor.", hs, d_masks, cfg["duration_predictor_layers"], False)
-        p_embs = conv1d_cl(p, "pitch_embed.0", ps)
-        e_embs = conv1d_cl(p, "energy_embed.0", es)
+        d_outs = duration_predictor(p, "duration_predictor.", hs, d_masks, cfg["duration_predictor_layers"], False, dropout=dropout,
+                                    rate=R["duration_predictor_dropout_rate"])
+        p_embs = _drop(dropout, dropout_site(6, 0, 7), conv1d_cl(p, "pitch_embed.0", ps), R["pitch_embed_dropout"])     # :220-247
+        e_embs = _drop(dropout, dropout_site(6, 0, 8), conv1d_cl(p, "energy_embed.0", es), R["energy_embed_dropout"])
         hs = hs + e_embs + p_embs
         hs_lr = length_regulator(hs, ds)
     if olens is not None and not is_inference:
         h_masks = make_non_pad_mask(olens, hs_lr.shape[1]).unsqueeze(-2)
     else:
         h_masks = None
-    zs = encoder(p, "decoder.", hs_lr, h_masks, cfg["dlayers"], nh, embed=False)
+    zs = encoder(p, "decoder.", hs_lr, h_masks, cfg["dlayers"], nh, embed=False, dropout=dropout, stack=1,
+                 rates=(R["transformer_dec_dropout_rate"], R["transformer_dec_positional_dropout_rate"], R["transformer_dec_attn_dropout_rate"]))
     before_outs = linear(p, "feat_out", zs).reshape(zs.shape[0], -1, p["feat_out.bias"].shape[0])
     if cfg["postnet_layers"] == 0:
         after_outs = before_outs
     else:
-        after_outs = before_outs + postnet(p, before_outs.transpose(1, 2), cfg["postnet_layers"], train_bn, new_stats).transpose(1, 2)
+        after_outs = before_outs + postnet(p, before_outs.transpose(1, 2), cfg["postnet_layers"], train_bn, new_stats, dropout,
+                                           R["postnet_dropout_rate"]).transpose(1, 2)
     if return_intermediates:
         return before_outs, after_outs, d_outs, p_outs, e_outs, dict(hs=hs, hs_lr=hs_lr, zs=zs)
     return before_outs, after_outs, d_outs, p_outs, e_outs
@@ -396,14 +482,16 @@ def synth_train_batch(seed, lengths, odim=80, idim=80, dur_range=(2, 12)):
 BUFFER_SUFFIXES = ("_mean", "_variance")
 
 
-def train_step_grads(p, cfg, batch, stop_gradient_from_pitch_predictor=True, stop_gradient_from_energy_predictor=False):
-    """-> (losses dict, grads dict keyed like p (trainable tensors only), new BN running stats)."""
+def train_step_grads(p, cfg, batch, stop_gradient_from_pitch_predictor=True, stop_gradient_from_energy_predictor=False,
+                     dropout=None, rates=None):
+    """-> (losses dict, grads dict keyed like p (trainable tensors only), new BN running stats).
+    dropout: None (all rates 0, the round-1 behaviour) or PhiloxDropout(seed, step) with `rates` (YAML_DROPOUT ...)."""
     q = {k: (v.clone().requires_grad_(True) if not k.endswith(BUFFER_SUFFIXES) else v.clone()) for k, v in p.items()}
     new_stats = {}
     out = fs2_forward(q, cfg, batch["text"], batch["text_lengths"], batch["speech_lengths"], batch["durations"], batch["pitch"],
                       batch["energy"], train_bn=True, new_stats=new_stats,
                       stop_gradient_from_pitch_predictor=stop_gradient_from_pitch_predictor,
-                      stop_gradient_from_energy_predictor=stop_gradient_from_energy_predictor)
+                      stop_gradient_from_energy_predictor=stop_gradient_from_energy_predictor, dropout=dropout, rates=rates)
     l1, dur, pitch, energy = fs2_loss(out[1], out[0], out[2], out[3], out[4], batch["speech"], batch["durations"], batch["pitch"],
                                       batch["energy"], batch["text_lengths"], batch["speech_lengths"])
     loss = l1 + dur + pitch + energy                                           # fastspeech2_updater.py:83

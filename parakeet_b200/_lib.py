@@ -112,6 +112,7 @@ def _declare(L):
         "pk_length_regulate_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
         "pk_scalar_conv_wgrad": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "pk_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+        "pk_dropout": [vp, vp, vp, i64, f32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp],
         "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
         "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],
         "pk_gated_activation": [vp, i64, i32, vp, vp, vp],

@@ -535,3 +535,64 @@ extern "C" int pk_adam(float* params, const float* grads, float* m, float* v, in
                                                    static_cast<float>(eps * c2), grad_scale);
   PK_LAUNCH_DONE()
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// Dropout (paddle.nn.Dropout, mode "upscale_in_train": y = x * mask / (1 - p) while training; the reference's FastSpeech2
+// applies it after the positional encodings, on the attention probabilities, after both sub-layers of every FFT block,
+// inside the position-wise feed-forward, in the predictors and in the postnet - SURVEY.md 8a).
+// The mask is never stored: element i keeps iff word (i & 3) of Philox4x32-10(counter = {i >> 2 (64 bit), site, step},
+// key = seed) is >= p * 2^32, so the backward pass regenerates it from (seed, step, site) with the same kernel applied
+// to the gradient.  oracle/fastspeech2.py restates the generator in numpy for the parity tests.
+// ----------------------------------------------------------------------------------------------------------------
+namespace pk {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
+                               long long n, uint32_t thresh, float scale, uint32_t seed_lo, uint32_t seed_hi, uint32_t site, uint32_t step,
+                               float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const long long blk = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;     // one Philox block = 4 elements
+  const long long i0 = blk * 4;
+  if (i0 >= n) return;
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, step, seed_lo, seed_hi, r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const long long i = i0 + e;
+    if (i >= n) break;
+    const float v = x ? x[i] : __bfloat162float(x_hi[i]) + __bfloat162float(x_lo[i]);
+    const float o = r[e] >= thresh ? v * scale : 0.f;
+    if (y) y[i] = o;
+    if (y_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(o, h, l);
+      y_hi[i] = h; y_lo[i] = l;
+    }
+  }
+}
+
+}  // namespace pk
+
+extern "C" int pk_dropout(const float* x, const void* x_hi, const void* x_lo, int64_t n, float p, uint64_t seed, uint32_t site,
+                          uint32_t step, float* y, void* y_hi, void* y_lo, pk_stream_t stream) {
+  using namespace pk;
+  PK_CHECK_ARG((x != nullptr) != (x_hi != nullptr) && (x_hi == nullptr) == (x_lo == nullptr), "give x (fp32) or x_hi + x_lo");
+  PK_CHECK_ARG((y || y_hi) && (y_hi == nullptr) == (y_lo == nullptr) && n > 0, "bad outputs / size");
+  PK_CHECK_ARG(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
+  const double t = static_cast<double>(p) * 4294967296.0;
+  const uint32_t thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+  const long long blocks4 = (n + 3) / 4;
+  dropout_kernel<<<nblk(blocks4, 256), 256, 0, PK_STREAM>>>(x, static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), n,
+                                                            thresh, 1.f / (1.f - p), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+                                                            site, step, y, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
+  PK_LAUNCH_DONE()
+}

@@ -124,6 +124,18 @@ class FastSpeech2(Layer):
         if unsupported:
             raise NotImplementedError("not in this round's hot-path scope: " + ", ".join(unsupported))
         self.idim, self.odim, self.adim, self.aheads = idim, odim, adim, aheads
+        # dropout is a training-time operation (identity in inference / eval forward): the rates are kept for
+        # training/fs2_step.py, which applies Philox masks at the reference's sites
+        self.dropout_rates = dict(
+            transformer_enc_dropout_rate=transformer_enc_dropout_rate,
+            transformer_enc_positional_dropout_rate=transformer_enc_positional_dropout_rate,
+            transformer_enc_attn_dropout_rate=transformer_enc_attn_dropout_rate,
+            transformer_dec_dropout_rate=transformer_dec_dropout_rate,
+            transformer_dec_positional_dropout_rate=transformer_dec_positional_dropout_rate,
+            transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
+            duration_predictor_dropout_rate=duration_predictor_dropout_rate, pitch_predictor_dropout=pitch_predictor_dropout,
+            energy_predictor_dropout=energy_predictor_dropout, postnet_dropout_rate=postnet_dropout_rate,
+            pitch_embed_dropout=pitch_embed_dropout, energy_embed_dropout=energy_embed_dropout)
         self.eos = idim - 1
         self.reduction_factor = reduction_factor
         self.padding_idx = 0

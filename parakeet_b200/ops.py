@@ -324,3 +324,18 @@ def relu_bwd(dy, y_split, want_f32=False):
 
 def axpy_(a, x, y):
     _lib.check(_lib.lib().pk_axpy(float(a), _ptr(x), x.numel(), _ptr(y), _stream()), "pk_axpy")
+
+
+def dropout(x, p, seed, site, step, out_f32=True, out_split=False, inplace=False):
+    """pk_dropout: x fp32 tensor or Split (any shape, contiguous) -> (y fp32 or None, y Split or None).  p == 0 is not a
+    special case here (callers skip the call)."""
+    is_split = isinstance(x, Split)
+    ref = x.hi if is_split else x
+    assert ref.is_contiguous()
+    n = ref.numel()
+    y = (x if (inplace and not is_split) else torch.empty(ref.shape, dtype=torch.float32, device=ref.device)) if out_f32 else None
+    ys = (x if (inplace and is_split) else Split.empty(tuple(ref.shape), ref.device)) if out_split else None
+    _lib.check(_lib.lib().pk_dropout(_ptr(None if is_split else x), _ptr(x.hi if is_split else None), _ptr(x.lo if is_split else None), n,
+                                     float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site), int(step), _ptr(y), _ptr(ys.hi if ys else None),
+                                     _ptr(ys.lo if ys else None), _stream()), "pk_dropout")
+    return y, ys

@@ -1,7 +1,8 @@
 """FastSpeech2 training step on B200 (reference: FastSpeech2Updater.update_core, parakeet/models/fastspeech2/
 fastspeech2_updater.py:51-99; data-parallel set-up examples/fastspeech2/train.py:51-56,135-139).
 
-    forward (train mode: BatchNorm uses batch statistics, dropout probability 0 as in SURVEY.md 8d)
+    forward (train mode: BatchNorm uses batch statistics; Dropout at the reference's sites with Philox masks that the backward
+    pass regenerates from (seed, step, site) - pk_dropout - so no mask is ever stored)
     -> FastSpeech2Loss (use_masking=True) -> backward -> mean all-reduce of the gradients over ranks (DataParallel)
     -> paddle.optimizer.Adam step.
 
@@ -45,7 +46,11 @@ def pack_dev(w):
 
 class FastSpeech2TrainStep:
     def __init__(self, model: FastSpeech2, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8,
-                 stop_gradient_from_pitch_predictor=None, stop_gradient_from_energy_predictor=None, process_group=None):
+                 stop_gradient_from_pitch_predictor=None, stop_gradient_from_energy_predictor=None, process_group=None,
+                 dropout=True, seed=0):
+        """dropout: True -> the model's constructor rates (the reference trains in model.train() mode), a dict of the
+        reference's rate keywords to override them, or False / None -> every rate 0 (deterministic step, parity tests).
+        seed: base seed of the Philox masks; every rank should pass its own (paddle seeds each process's generator)."""
         if not model.device.type == "cuda":
             raise _lib.PkError("training needs a CUDA device (no CPU fallback)")
         self.m = model
@@ -62,6 +67,13 @@ class FastSpeech2TrainStep:
         self.adam_v = torch.zeros(self.buffers.total, dtype=torch.float32, device=dev)
         model._packed = None
         self.step_count = 0
+        if dropout is True:
+            self.rates = dict(model.dropout_rates)
+        elif isinstance(dropout, dict):
+            self.rates = {**model.dropout_rates, **dropout}
+        else:
+            self.rates = {k: 0.0 for k in model.dropout_rates}
+        self.seed = int(seed)
         # EXPERIMENTAL (PK_TRAIN_GRAPH=1, default off, not validated on a GPU yet): forward + backward replayed as a CUDA graph per
         # batch shape (B, Tmax, Lmax) once a shape repeats (bucketed samplers); the step is host-bound (~600 launches).
         self._fb_graphs = GraphRunner(max_graphs=16)
@@ -89,6 +101,18 @@ class FastSpeech2TrainStep:
         if v is None:
             v = self._packs[key] = fn()
         return v
+
+    @staticmethod
+    def site(stack, layer, kind):
+        """stack: 0 encoder, 1 decoder, 2 pitch, 3 energy, 4 duration predictor, 5 postnet; kind: 0 positional encoding,
+        1 attention probabilities, 2 attention sub-layer output, 3 feed-forward hidden, 4 feed-forward sub-layer output,
+        5 predictor layer, 6 postnet layer; (6, 0, 7) / (6, 0, 8): pitch / energy embedding
+        (oracle/fastspeech2.py: dropout_site restates this numbering)."""
+        return stack * 1000 + layer * 10 + kind
+
+    def drop(self, x, p, site, **kw):
+        """Forward AND backward: the mask depends only on (seed, step, site, element index)."""
+        return ops.dropout(x, p, self.seed, site, self.step_count + 1, **kw)
 
     def w_fwd(self, name, kind):
         w = self.P(name)
@@ -155,6 +179,9 @@ class FastSpeech2TrainStep:
     # ------------------------------------------------------------------------------------------------------------
     def stack_fwd(self, x, pre, n_layers, key_lens):
         m = self.m
+        sid = 0 if pre == "encoder." else 1
+        tag = "enc" if sid == 0 else "dec"
+        r_layer, r_attn = self.rates[f"transformer_{tag}_dropout_rate"], self.rates[f"transformer_{tag}_attn_dropout_rate"]
         B, T, A = x.shape
         H, dk = m.aheads, A // m.aheads
         Tp = _ceil64(T)
@@ -176,21 +203,35 @@ class FastSpeech2TrainStep:
             ops.batched_matmul_nt(qkv, qkv, batch=B, heads=H, m=T, n=T, k=dk, a_spec=q_spec, b_spec=k_spec, scale=1.0 / math.sqrt(dk),
                                   y_f32=s_buf, y_batch_stride=H * T * Tp, y_head_stride=T * Tp, y_ld=Tp)
             c["p"] = ops.masked_softmax(s_buf, key_lens, B, H, T, T)
+            c["pd"] = self.drop(c["p"], r_attn, self.site(sid, i, 1), out_f32=False, out_split=True)[1] if r_attn > 0 else c["p"]
             vt = ops.transpose_heads(qkv, col0=2 * A, dk=dk, heads=H, ld_dst=Tp)
             ctx = Split.empty((B, T, A), x.device)
             p_spec = dict(rows=T, cols=Tp, ld=Tp, batch_stride=T * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
             v_spec = dict(rows=dk, cols=Tp, ld=Tp, batch_stride=dk * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
-            ops.batched_matmul_nt(c["p"], vt, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=p_spec, b_spec=v_spec, y_split=ctx,
+            ops.batched_matmul_nt(c["pd"], vt, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=p_spec, b_spec=v_spec, y_split=ctx,
                                   y_batch_stride=T * A, y_head_stride=dk, y_ld=A)
             c["ctx"] = ctx
-            x1, _ = self.layer_fwd(ctx, q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin", residual=x)
+            if r_layer > 0:      # x1 = x + dropout(attention): the residual add cannot ride in the GEMM epilogue any more
+                a_out, _ = self.layer_fwd(ctx, q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin")
+                self.drop(a_out, r_layer, self.site(sid, i, 2), inplace=True)
+                ops.axpy_(1.0, x, a_out)
+                x1 = a_out
+            else:
+                x1, _ = self.layer_fwd(ctx, q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin", residual=x)
             c["x1"] = x1
             _, c["h2"] = ops.layer_norm(x1, self.P(q + "norm2.weight"), self.P(q + "norm2.bias"))
             _, c["u"] = self.layer_fwd(c["h2"], q + "feed_forward.w_1.weight", q + "feed_forward.w_1.bias", kind, act="relu", f32=False, split=True)
-            x, _ = self.layer_fwd(c["u"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind, residual=x1)
+            c["ud"] = self.drop(c["u"], r_layer, self.site(sid, i, 3), out_f32=False, out_split=True)[1] if r_layer > 0 else c["u"]
+            if r_layer > 0:
+                f_out, _ = self.layer_fwd(c["ud"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind)
+                self.drop(f_out, r_layer, self.site(sid, i, 4), inplace=True)
+                ops.axpy_(1.0, x1, f_out)
+                x = f_out
+            else:
+                x, _ = self.layer_fwd(c["u"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind, residual=x1)
             ctxs.append(c)
         y, ys = ops.layer_norm(x, self.P(pre + "after_norm.weight"), self.P(pre + "after_norm.bias"), want_f32=True, want_split=True)
-        return y, ys, dict(layers=ctxs, x_last=x, pre=pre, n=n_layers)
+        return y, ys, dict(layers=ctxs, x_last=x, pre=pre, n=n_layers, sid=sid, r_layer=r_layer, r_attn=r_attn)
 
     def stack_bwd(self, dy, S):
         """dy: gradient w.r.t. the after_norm output (fp32).  Returns the gradient w.r.t. the stack input."""
@@ -204,16 +245,21 @@ class FastSpeech2TrainStep:
         dx = torch.empty_like(dy)
         ops.layer_norm_bwd(S["x_last"], self.P(pre + "after_norm.weight"), dy, dx, False, self.grads[pre + "after_norm.weight"],
                            self.grads[pre + "after_norm.bias"])
+        sid, r_layer, r_attn = S["sid"], S["r_layer"], S["r_attn"]
         for i in reversed(range(S["n"])):
             q = f"{pre}encoders.{i}."
             c = S["layers"][i]
-            # x2 = x1 + conv2(relu(conv1(LN2(x1))))
-            du = self.layer_bwd(dx, c["u"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind)
+            # x2 = x1 + drop(conv2(drop(relu(conv1(LN2(x1))))))
+            dsub = self.drop(dx, r_layer, self.site(sid, i, 4))[0] if r_layer > 0 else dx
+            du = self.layer_bwd(dsub, c["ud"], q + "feed_forward.w_2.weight", q + "feed_forward.w_2.bias", kind)
+            if r_layer > 0:
+                self.drop(du, r_layer, self.site(sid, i, 3), inplace=True)
             du_f, _ = ops.relu_bwd(du, c["u"], want_f32=True)
             dh2 = self.layer_bwd(du_f, c["h2"], q + "feed_forward.w_1.weight", q + "feed_forward.w_1.bias", kind)
             ops.layer_norm_bwd(c["x1"], self.P(q + "norm2.weight"), dh2, dx, True, self.grads[q + "norm2.weight"], self.grads[q + "norm2.bias"])
-            # x1 = x0 + out_proj(attention(LN1(x0)))
-            dctx = self.layer_bwd(dx, c["ctx"], q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin")
+            # x1 = x0 + drop(out_proj(attention(LN1(x0))))
+            dsub = self.drop(dx, r_layer, self.site(sid, i, 2))[0] if r_layer > 0 else dx
+            dctx = self.layer_bwd(dsub, c["ctx"], q + "self_attn.linear_out.weight", q + "self_attn.linear_out.bias", "lin")
             dctx_s = Split.from_f32(dctx)
             qkv, p = c["qkv"], c["p"]
             ld = 3 * A
@@ -222,7 +268,9 @@ class FastSpeech2TrainStep:
             v_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=2 * A, colh=dk)
             dp = torch.zeros(B * H, T, Tp, dtype=torch.float32, device=dev)
             ops.batched_matmul_nt(dctx_s, qkv, batch=B, heads=H, m=T, n=T, k=dk, a_spec=o_spec, b_spec=v_spec, y_f32=dp,
-                                  y_batch_stride=H * T * Tp, y_head_stride=T * Tp, y_ld=Tp)                       # dP = dO V^T
+                                  y_batch_stride=H * T * Tp, y_head_stride=T * Tp, y_ld=Tp)                       # d(drop(P)) = dO V^T
+            if r_attn > 0:
+                self.drop(dp, r_attn, self.site(sid, i, 1), inplace=True)                                         # -> dP
             ds = ops.softmax_bwd(p, dp, T, 1.0 / math.sqrt(dk))                                                  # includes the 1/sqrt(dk)
             z_spec = dict(rows=T, cols=Tp, ld=Tp, batch_stride=T * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
             d_spec = dict(rows=dk, cols=Tp, ld=Tp, batch_stride=dk * Tp, batches=B * H, bmul=H, hmul=1, col0=0, colh=0)
@@ -240,7 +288,7 @@ class FastSpeech2TrainStep:
                                          r_out=T, dst=Split(dst.hi[:, h], dst.lo[:, h]), dst_zstride=H * dk * Tp, ld_dst=Tp)
                 return dst
 
-            pt, dot = t_sq(p), t_heads(dctx_s, A, 0)
+            pt, dot = t_sq(c["pd"]), t_heads(dctx_s, A, 0)                                                        # dV uses the dropped P
             ops.batched_matmul_nt(pt, dot, batch=B, heads=H, m=T, n=dk, k=Tp, a_spec=z_spec, b_spec=d_spec, y_f32=dqkv[:, :, 2 * A:],
                                   y_batch_stride=T * ld, y_head_stride=dk, y_ld=ld)                               # dV = P^T dO
             kt = t_heads(qkv, ld, A)
@@ -277,14 +325,18 @@ class FastSpeech2TrainStep:
     # predictors
     # ------------------------------------------------------------------------------------------------------------
     def pred_fwd(self, pre, n_layers, hs_split):
+        sid, rate = {"pitch_predictor.": (2, self.rates["pitch_predictor_dropout"]), "energy_predictor.": (3, self.rates["energy_predictor_dropout"]),
+                     "duration_predictor.": (4, self.rates["duration_predictor_dropout_rate"])}[pre]
         saved, h = [], hs_split
         for i in range(n_layers):
             y, ys = self.layer_fwd(h, f"{pre}conv.{i}.0.weight", f"{pre}conv.{i}.0.bias", "conv", act="relu", f32=True, split=True)
             _, hn = ops.layer_norm(y, self.P(f"{pre}conv.{i}.2.weight"), self.P(f"{pre}conv.{i}.2.bias"))
+            if rate > 0:
+                hn = self.drop(hn, rate, self.site(sid, i, 5), out_f32=False, out_split=True)[1]
             saved.append(dict(x=h, y=y, ys=ys))
             h = hn
         out, _ = self.layer_fwd(h, pre + "linear.weight", pre + "linear.bias", "lin")
-        return out, dict(layers=saved, h_last=h, pre=pre)
+        return out, dict(layers=saved, h_last=h, pre=pre, sid=sid, rate=rate)
 
     def pred_bwd(self, dout, S, need_dx=True):
         pre = S["pre"]
@@ -292,6 +344,8 @@ class FastSpeech2TrainStep:
         n = len(S["layers"])
         for i in reversed(range(n)):
             c = S["layers"][i]
+            if S["rate"] > 0:
+                self.drop(g, S["rate"], self.site(S["sid"], i, 5), inplace=True)
             dy = torch.empty_like(g)
             ops.layer_norm_bwd(c["y"], self.P(f"{pre}conv.{i}.2.weight"), g, dy, False, self.grads[f"{pre}conv.{i}.2.weight"],
                                self.grads[f"{pre}conv.{i}.2.bias"])
@@ -319,7 +373,10 @@ class FastSpeech2TrainStep:
         ys = batch["speech"].to(dev, torch.float32).contiguous()
         A, odim = m.adim, m.odim
         # ---- forward (train mode) ----
+        R = self.rates
         x = ops.embed_pe(text, self.P("encoder.embed.0.weight"), None, self.P("encoder.embed.1.alpha"), None, m.padding_idx)
+        if R["transformer_enc_positional_dropout_rate"] > 0:
+            self.drop(x, R["transformer_enc_positional_dropout_rate"], self.site(0, 0, 0), inplace=True)
         hs, hs_split, S_enc = self.stack_fwd(x, "encoder.", m.elayers, ilens)
         p_raw, S_p = self.pred_fwd("pitch_predictor.", m.cfg["pitch"][0], hs_split)
         e_raw, S_e = self.pred_fwd("energy_predictor.", m.cfg["energy"][0], hs_split)
@@ -328,11 +385,29 @@ class FastSpeech2TrainStep:
         e_outs = ops.mask_rows_(e_raw.reshape(B, T).clone(), ilens)
         d_outs = ops.mask_rows_(d_raw.reshape(B, T).clone(), ilens)
         pe_w, ee_w = self.P("pitch_embed.0.weight"), self.P("energy_embed.0.weight")
-        hs2 = ops.variance_embed_add(hs, ps, es, pe_w.reshape(A, -1), self.P("pitch_embed.0.bias"), ee_w.reshape(A, -1),
-                                     self.P("energy_embed.0.bias"), None)
+        r_pe, r_ee = R["pitch_embed_dropout"], R["energy_embed_dropout"]
+        if r_pe > 0 or r_ee > 0:
+            # Sequential(Conv1D, Dropout) (fastspeech2.py:220-247): the two embeddings one at a time (the fused kernel with the
+            # other embedding's weights zeroed), each through its own mask, then hs + e_embs + p_embs
+            zw_p, zw_e = torch.zeros_like(pe_w.reshape(A, -1)), torch.zeros_like(ee_w.reshape(A, -1))
+            zb, z0 = torch.zeros(A, device=dev), torch.zeros_like(hs)
+            p_emb = ops.variance_embed_add(z0, ps, es, pe_w.reshape(A, -1), self.P("pitch_embed.0.bias"), zw_e, zb, None)
+            e_emb = ops.variance_embed_add(z0, ps, es, zw_p, zb, ee_w.reshape(A, -1), self.P("energy_embed.0.bias"), None)
+            if r_pe > 0:
+                self.drop(p_emb, r_pe, self.site(6, 0, 7), inplace=True)
+            if r_ee > 0:
+                self.drop(e_emb, r_ee, self.site(6, 0, 8), inplace=True)
+            hs2 = hs.clone()
+            ops.axpy_(1.0, e_emb, hs2)
+            ops.axpy_(1.0, p_emb, hs2)
+        else:
+            hs2 = ops.variance_embed_add(hs, ps, es, pe_w.reshape(A, -1), self.P("pitch_embed.0.bias"), ee_w.reshape(A, -1),
+                                         self.P("energy_embed.0.bias"), None)
         t_dec = ys.shape[1]
         hs_lr, _ = ops.length_regulate(hs2, ds, t_dec)
         xd = ops.embed_pe(None, None, hs_lr, self.P("decoder.embed.0.alpha"), None)
+        if R["transformer_dec_positional_dropout_rate"] > 0:
+            self.drop(xd, R["transformer_dec_positional_dropout_rate"], self.site(1, 0, 0), inplace=True)
         zs, zs_split, S_dec = self.stack_fwd(xd, "decoder.", m.dlayers, olens)
         before, before_split = self.layer_fwd(zs_split, "feat_out.weight", "feat_out.bias", "lin", f32=True, split=True)
         post, h = [], before_split
@@ -351,10 +426,13 @@ class FastSpeech2TrainStep:
                                              0 if last else 2, 0.9, _ptr(m._params[q + "_mean"]), _ptr(m._params[q + "_variance"]),
                                              _ptr(self.sums), _ptr(y), _ptr(ysplit.hi) if ysplit else None,
                                              _ptr(ysplit.lo) if ysplit else None, _ptr(mean), _ptr(rstd), st), "pk_batch_norm_train")
-            post.append(dict(x=h, conv=conv_out, y=y, mean=mean, rstd=rstd))
+            yd = y
+            if R["postnet_dropout_rate"] > 0:                # Dropout closes every postnet layer (tacotron2/decoder.py:144-180)
+                yd, ysplit = self.drop(y, R["postnet_dropout_rate"], self.site(5, i, 6), out_f32=True, out_split=not last)
+            post.append(dict(x=h, conv=conv_out, y=y, yd=yd, mean=mean, rstd=rstd))
             h = ysplit
         after = before.clone()
-        ops.axpy_(1.0, post[-1]["y"], after)
+        ops.axpy_(1.0, post[-1]["yd"], after)
         # ---- loss and its gradient ----
         losses = torch.empty(4, dtype=torch.float32, device=dev)
         ws = torch.empty(12, dtype=torch.float32, device=dev)
@@ -373,6 +451,8 @@ class FastSpeech2TrainStep:
             q = f"postnet.postnet.{i}.1."
             cdim = c["conv"].shape[-1]
             dconv = torch.empty_like(c["conv"])
+            if R["postnet_dropout_rate"] > 0:
+                g = self.drop(g, R["postnet_dropout_rate"], self.site(5, i, 6))[0]
             _lib.check(L.pk_batch_norm_bwd(_ptr(c["conv"]), _ptr(g), _ptr(c["y"]), _ptr(c["mean"]), _ptr(c["rstd"]), _ptr(self.P(q + "weight")),
                                            0 if last else 2, rows, cdim, _ptr(self.sums), _ptr(dconv), st), "pk_batch_norm_bwd")
             self.grads[q + "bias"].copy_(self.sums[:cdim])
@@ -382,13 +462,17 @@ class FastSpeech2TrainStep:
         ops.axpy_(1.0, g_before, g)                            # direct L1 on `before`
         dzs = self.layer_bwd(g, zs_split, "feat_out.weight", "feat_out.bias", "lin")
         dxd = self.stack_bwd(dzs, S_dec)
+        if R["transformer_dec_positional_dropout_rate"] > 0:
+            self.drop(dxd, R["transformer_dec_positional_dropout_rate"], self.site(1, 0, 0), inplace=True)
         _lib.check(L.pk_embed_pe_bwd(None, _ptr(dxd), 0, 0, B, t_dec, A, None, _ptr(self.grads["decoder.embed.0.alpha"]), st), "pk_embed_pe_bwd")
         dhs = torch.empty(B, T, A, dtype=torch.float32, device=dev)
         _lib.check(L.pk_length_regulate_bwd(_ptr(dxd), _ptr(ds), B, T, A, t_dec, _ptr(dhs), st), "pk_length_regulate_bwd")
         kp, ke = pe_w.shape[-1], ee_w.shape[-1]
-        _lib.check(L.pk_scalar_conv_wgrad(_ptr(dhs), _ptr(ps), B, T, A, kp, _ptr(self.grads["pitch_embed.0.weight"]),
+        d_pe = self.drop(dhs, r_pe, self.site(6, 0, 7))[0] if r_pe > 0 else dhs
+        d_ee = self.drop(dhs, r_ee, self.site(6, 0, 8))[0] if r_ee > 0 else dhs
+        _lib.check(L.pk_scalar_conv_wgrad(_ptr(d_pe), _ptr(ps), B, T, A, kp, _ptr(self.grads["pitch_embed.0.weight"]),
                                           _ptr(self.grads["pitch_embed.0.bias"]), st), "pk_scalar_conv_wgrad")
-        _lib.check(L.pk_scalar_conv_wgrad(_ptr(dhs), _ptr(es), B, T, A, ke, _ptr(self.grads["energy_embed.0.weight"]),
+        _lib.check(L.pk_scalar_conv_wgrad(_ptr(d_ee), _ptr(es), B, T, A, ke, _ptr(self.grads["energy_embed.0.weight"]),
                                           _ptr(self.grads["energy_embed.0.bias"]), st), "pk_scalar_conv_wgrad")
         gd = self.pred_bwd(g_d, S_d)
         ops.axpy_(1.0, gd, dhs)
@@ -399,6 +483,8 @@ class FastSpeech2TrainStep:
         if not self.sg_pitch:
             ops.axpy_(1.0, gp, dhs)
         dx = self.stack_bwd(dhs, S_enc)
+        if R["transformer_enc_positional_dropout_rate"] > 0:
+            self.drop(dx, R["transformer_enc_positional_dropout_rate"], self.site(0, 0, 0), inplace=True)
         _lib.check(L.pk_embed_pe_bwd(_ptr(text), _ptr(dx), m.idim, m.padding_idx, B, T, A, _ptr(self.grads["encoder.embed.0.weight"]),
                                      _ptr(self.grads["encoder.embed.1.alpha"]), st), "pk_embed_pe_bwd")
         return losses

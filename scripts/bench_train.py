@@ -23,7 +23,7 @@ m = FastSpeech2(80, 80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, d
                 postnet_layers=5, postnet_filts=5, postnet_chans=256, pitch_predictor_layers=5, pitch_predictor_chans=256,
                 pitch_predictor_kernel_size=5, pitch_embed_kernel_size=1, energy_predictor_layers=2, energy_predictor_chans=256,
                 energy_predictor_kernel_size=3, energy_embed_kernel_size=1, stop_gradient_from_pitch_predictor=True, device=dev, seed=1)  # same seed on every rank
-ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=False)
 g = torch.Generator().manual_seed(5 + rank)              # every rank gets its own shard of the (synthetic) data
 B = args.per_gpu_batch
 lengths = torch.randint(60, 141, (B,), generator=g).tolist()

@@ -9,7 +9,7 @@ batch = ofs.synth_train_batch(5, [9, 14, 11], dur_range=(1, 4))
 losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
 m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device="cuda")
 m.set_state_dict(params)
-ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=False)
 losses = ts.forward_backward(batch)
 print("losses", [float(v) for v in losses], losses_ref)
 rows = []

@@ -96,7 +96,7 @@ def test_fs2_training_step_gradients_and_update(cuda):
     losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
     m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
     m.set_state_dict(params)
-    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=False)
     losses = ts.forward_backward(batch)
     got = [float(v) for v in losses]
     ref = [losses_ref[k] for k in ("l1_loss", "duration_loss", "pitch_loss", "energy_loss")]
@@ -141,7 +141,7 @@ def test_fs2_training_reduces_loss(cuda):
     m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
     m.set_state_dict(ofs.synth_params(1))
     batch = ofs.synth_train_batch(6, [12, 9, 15, 10], dur_range=(1, 4))
-    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=False)
     first = float(ts.step(batch).sum())
     for _ in range(7):
         last = float(ts.step(batch).sum())
@@ -168,7 +168,7 @@ def test_fs2_training_step_cfg5_shape_vs_oracle(cuda):
     losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
     m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
     m.set_state_dict(params)
-    ts = FastSpeech2TrainStep(m, learning_rate=1e-3)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=False)
     got = [float(v) for v in ts.forward_backward(batch)]
     ref = [losses_ref[k] for k in ("l1_loss", "duration_loss", "pitch_loss", "energy_loss")]
     assert np.allclose(got, ref, rtol=1e-3), (got, ref)
@@ -204,7 +204,7 @@ def test_fs2_three_steps_follow_the_oracle_adam_trajectory(cuda):
         p_ref = {**p_ref, **new, **stats}
     m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda)
     m.set_state_dict(params)
-    ts = FastSpeech2TrainStep(m, learning_rate=lr)
+    ts = FastSpeech2TrainStep(m, learning_rate=lr, dropout=False)
     loss_got = [float(ts.step(batch).sum()) for _ in range(3)]
     assert np.allclose(loss_got, loss_ref, rtol=2e-3), (loss_got, loss_ref)
     sd = m.state_dict()
@@ -231,3 +231,69 @@ def test_fs2_three_steps_follow_the_oracle_adam_trajectory(cuda):
     assert sum(e > 5e-2 for _, e, _ in worst) <= 0.08 * len(worst), worst[:24]
     # and the loss went down along the way
     assert loss_got[2] < loss_got[0]
+
+
+def test_dropout_kernel_matches_the_numpy_philox_restatement_and_its_statistics(cuda):
+    """pk_dropout against oracle.PhiloxDropout (numpy Philox4x32-10, itself pinned to the Random123 known answers in
+    tests/test_oracle_cpu.py): identical masks, upscale_in_train scaling, split-plane input / output, and keep-rate statistics."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 37, 101, generator=g)                             # 11 211 elements: not a multiple of 4
+    for p, site, step, seed in ((0.2, 1021, 3, 12345), (0.5, 5046, 1, (1 << 40) + 17), (0.1, 0, 7, 0)):
+        ref = ofs.PhiloxDropout(seed, step)(site, x, p)
+        y, ys = ops.dropout(x.to(cuda), p, seed, site, step, out_f32=True, out_split=True)
+        assert torch.equal((y == 0).cpu(), ref == 0)
+        assert torch.allclose(y.cpu(), ref, rtol=1e-6, atol=0)
+        assert torch.allclose(ys.float().cpu(), ref, rtol=2e-5, atol=1e-6)
+        y2, _ = ops.dropout(ops.Split.from_f32(x.to(cuda)), p, seed, site, step)          # split input
+        assert torch.allclose(y2.cpu(), ref, rtol=2e-5, atol=1e-6)
+    big = torch.ones(1 << 22, device=cuda)
+    for p in (0.1, 0.2, 0.5):
+        y, _ = ops.dropout(big, p, 99, 4, 1)
+        keep = float((y != 0).float().mean())
+        assert abs(keep - (1 - p)) < 4 * (p * (1 - p) / big.numel()) ** 0.5 + 1e-4, (p, keep)    # 4 sigma
+        assert abs(float(y.mean()) - 1.0) < 5e-3                                                  # upscale_in_train keeps the mean
+    a, _ = ops.dropout(big, 0.5, 99, 4, 1)
+    b, _ = ops.dropout(big, 0.5, 99, 5, 1)                                # another site: an independent mask
+    c, _ = ops.dropout(big, 0.5, 99, 4, 2)                                # another step: an independent mask
+    assert 0.45 < float(((a != 0) == (b != 0)).float().mean()) < 0.55 and 0.45 < float(((a != 0) == (c != 0)).float().mean()) < 0.55
+
+
+def test_fs2_training_step_with_the_shipped_dropout_rates_vs_oracle(cuda):
+    """The reference's recipe (conf/default.yaml:56-74: 0.2 on the six transformer rates, 0.5 in the pitch / energy predictors
+    and the postnet, 0.1 in the duration predictor): forward losses, gradients and BatchNorm statistics of one step against the
+    oracle applying the SAME Philox masks at the reference's dropout sites, and the masks change from step to step."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    params = ofs.synth_params(1)
+    batch = ofs.synth_train_batch(61, _cfg5_lengths(4, seed=62))
+    rates = dict(ofs.YAML_DROPOUT, pitch_embed_dropout=0.3)             # + one of the embedding dropouts the yaml leaves at 0
+    seed = 2024
+    losses_ref, grads_ref, stats_ref = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True,
+                                                             dropout=ofs.PhiloxDropout(seed, 1), rates=rates)
+    losses_nodrop, _, _ = ofs.train_step_grads(params, None, batch, stop_gradient_from_pitch_predictor=True)
+    assert abs(losses_ref["loss"] - losses_nodrop["loss"]) > 1e-2                      # the masks do something
+    m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda, **rates)
+    m.set_state_dict(params)
+    ts = FastSpeech2TrainStep(m, learning_rate=1e-3, dropout=True, seed=seed)
+    got = [float(v) for v in ts.forward_backward(batch)]
+    ref = [losses_ref[k] for k in ("l1_loss", "duration_loss", "pitch_loss", "energy_loss")]
+    assert np.allclose(got, ref, rtol=1e-3), (got, ref)
+    errs = []
+    for k, gref in grads_ref.items():
+        g, r = ts.grads[k].detach().double().cpu(), gref.double()
+        if k.endswith("self_attn.linear_k.bias"):        # true gradient 0 (softmax ignores a per-row shift): rounding noise in both
+            assert g.abs().max().item() < 1e-4 and r.abs().max().item() < 1e-4, k
+            continue
+        if (g - r).norm().item() > 1e-7:
+            errs.append((k, (g - r).norm().item() / max(r.norm().item(), 1e-12)))
+    errs.sort(key=lambda t: -t[1])
+    assert not errs or errs[0][1] < 2e-2, errs[:8]
+    assert sum(e > 5e-3 for _, e in errs) <= 0.1 * len(grads_ref), errs[:24]
+    for k, v in stats_ref.items():
+        assert _close(m.state_dict()[k], v), k
+    first = float(ts.step(batch).sum())                                    # step 1 (same masks as above), then step 2: new masks
+    second_fb = [float(v) for v in ts.forward_backward(batch)]
+    assert np.allclose(first, sum(ref), rtol=1e-3) and abs(sum(second_fb) - first) > 1e-3

@@ -348,3 +348,18 @@ def test_pad_masks_against_vectors_produced_by_the_reference_code():
         lens = torch.from_numpy(g[f"mask_len{i}"])
         assert np.array_equal(ofs.make_pad_mask(lens).numpy(), g[f"mask_pad{i}"])
         assert np.array_equal(ofs.make_non_pad_mask(lens).numpy(), g[f"mask_nonpad{i}"])
+
+
+def test_philox_restatement_known_answers():
+    """oracle.fastspeech2.philox4x32_10 against the Random123 known-answer vectors for philox4x32-10 (kat_vectors)."""
+    from oracle import fastspeech2 as ofs
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = ofs.philox4x32_10(*[np.array([c]) for c in ctr], *key)
+        assert tuple(int(v[0]) for v in got) == want
+    d = ofs.PhiloxDropout(5, 1)
+    x = torch.ones(4, 1000)
+    y = d(17, x, 0.25)
+    assert abs(float((y != 0).float().mean()) - 0.75) < 0.03 and torch.all((y == 0) | (y - 1 / 0.75).abs().lt(1e-6))
