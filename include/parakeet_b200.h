@@ -255,6 +255,15 @@ int pk_layer_norm(const float* x, const float* gamma, const float* beta, float e
  * keys >= key_lens[b] and the padding columns [keys, ld) get probability 0; output split planes, same layout. */
 int pk_masked_softmax(const float* s, const int32_t* key_lens, int32_t batch, int32_t heads, int32_t rows, int32_t keys,
                       int32_t ld, void* p_hi, void* p_lo, pk_stream_t stream);
+/* Fused scaled-dot-product attention of an FFT block (attention.py:88-131: scores = q k^T / sqrt(d_k), masked_fill(min) ->
+ * softmax -> masked_fill(0), p_attn . v, heads merged) in one kernel: scores and probabilities stay in tensor memory.
+ *   qkv planes (batch, t, 3 * heads * dk): [q | k | v] of the fused QKV projection, head h in columns h * dk of each third;
+ *   vt planes (batch * heads, dk, tp): v transposed per head (pk_transpose_heads), columns >= t zero; both pairs of planes
+ *   from one allocation each (lo after hi).  key_lens / row_lens: device int32 [batch] or NULL (keys >= key_lens[b] masked;
+ *   query rows >= row_lens[b] written as zero).  ctx planes (batch, t, heads * dk).  dk in {64, 128, 192}. */
+int pk_fused_attention(const void* qkv_hi, const void* qkv_lo, const void* vt_hi, const void* vt_lo, int32_t batch, int32_t t,
+                       int32_t heads, int32_t dk, int32_t tp, const int32_t* key_lens, const int32_t* row_lens, float scale,
+                       void* ctx_hi, void* ctx_lo, pk_stream_t stream);
 /* (batch, t, ld_src)[.., col0 + h*dk + d] -> (batch*heads, dk, ld_dst)[.., d, t] (zero-filled for t in [t, ld_dst)):
  * the value matrix in K-major form for the P.V product (attention.py:126). */
 int pk_transpose_heads(const void* src_hi, const void* src_lo, int32_t batch, int32_t t, int32_t ld_src, int32_t col0,

@@ -93,6 +93,7 @@ def _declare(L):
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],
         "pk_masked_softmax": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
         "pk_transpose_heads": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+        "pk_fused_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp],
         "pk_duration_post": [vp, vp, i32, i32, f32, vp, vp, vp],
         "pk_duration_scale": [vp, f32, i64, vp, vp],
         "pk_mask_rows": [vp, vp, i32, i32, i32, vp],

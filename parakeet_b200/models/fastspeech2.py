@@ -16,6 +16,7 @@ Scope of this round: inference-mode arithmetic (dropout = identity, BatchNorm us
 backward pass are not implemented and raise NotImplementedError.
 """
 import math
+import os
 from typing import Dict, Optional, Sequence, Tuple  # noqa: F401
 
 import torch
@@ -295,11 +296,21 @@ class FastSpeech2(Layer):
         H, dk = self.aheads, A // self.aheads
         Tp = (T + 63) // 64 * 64
         dev = x.device
-        s_buf = torch.empty(B * H, T, Tp, dtype=torch.float32, device=dev)
+        fused = dk in (64, 128, 192) and os.environ.get("PK_FUSED_ATTN", "1") != "0"
+        s_buf = torch.empty(B * H, T, Tp, dtype=torch.float32, device=dev) if not fused else None
         ctx = Split.empty((B, T, A), dev)
         for lay in layers:
             _, h = ops.layer_norm(x, *lay["n1"], lens=row_lens)
             _, qkv = ops.conv_gemm(h, lay["wqkv"], n=3 * A, k=A, bias=lay["bqkv"], lens=row_lens, out_f32=False, out_split=True)
+            if fused:
+                # scores, key mask, softmax and P.V in one kernel (csrc/attention.cu); no (B*H, T, T) tensor in HBM
+                ops.fused_attention(qkv, H, key_lens=key_lens, row_lens=row_lens, ctx=ctx)
+                x, _ = ops.conv_gemm(ctx, lay["wo"], n=A, k=A, bias=lay["bo"], residual=x, lens=row_lens)
+                _, h = ops.layer_norm(x, *lay["n2"], lens=row_lens)
+                _, u = ops.conv_gemm(h, lay["w1"], n=lay["units"], k=A, taps=self.ffn_k, bias=lay["b1"], act="relu", lens=row_lens,
+                                     out_f32=False, out_split=True)
+                x, _ = ops.conv_gemm(u, lay["w2"], n=A, k=lay["units"], taps=self.ffn_k, bias=lay["b2"], residual=x, lens=row_lens)
+                continue
             ld = 3 * A
             q_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=0, colh=dk)
             k_spec = dict(rows=T, cols=ld, ld=ld, batch_stride=T * ld, batches=B, bmul=1, hmul=0, col0=A, colh=dk)

@@ -244,6 +244,22 @@ def transpose_heads(src, col0, dk, heads, ld_dst):
     return dst
 
 
+def fused_attention(qkv, heads, key_lens=None, row_lens=None, ctx=None):
+    """qkv Split (B, T, 3A) -> ctx Split (B, T, A): softmax(q k^T / sqrt(d_k), key mask) v per head, one kernel
+    (pk_fused_attention) after the per-head transpose of v."""
+    B, T, ld = qkv.hi.shape
+    A = ld // 3
+    dk = A // heads
+    Tp = (T + 63) // 64 * 64
+    vt = transpose_heads(qkv, col0=2 * A, dk=dk, heads=heads, ld_dst=Tp)
+    if ctx is None:
+        ctx = Split.empty((B, T, A), qkv.hi.device)
+    _lib.check(_lib.lib().pk_fused_attention(_ptr(qkv.hi), _ptr(qkv.lo), _ptr(vt.hi), _ptr(vt.lo), B, T, heads, dk, Tp, _ptr(key_lens),
+                                             _ptr(row_lens), 1.0 / math.sqrt(dk), _ptr(ctx.hi), _ptr(ctx.lo), _stream()),
+               "pk_fused_attention")
+    return ctx
+
+
 def duration_post(x, lens, offset=1.0):
     B, T = x.shape
     x = x.contiguous()

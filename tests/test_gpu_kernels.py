@@ -140,3 +140,27 @@ def test_row_kernels(cuda):
     z = torch.randn(7, 80, generator=gen)
     assert rel_err(ops.zscore(z.to(cuda), mu.to(cuda), sg.to(cuda)), (z - mu) / sg) < 1e-6
     assert rel_err(ops.zscore(z.to(cuda), mu.to(cuda), sg.to(cuda), inverse=True), z * sg + mu) < 1e-6
+
+
+def test_fused_attention_vs_fp64(cuda):
+    """pk_fused_attention (scores, key-padding mask, softmax, P.V in one kernel) against an fp64 evaluation of
+    attention.py:88-131 on the same split-bf16 inputs: ragged key lengths, query tiles past an utterance's end, T not a
+    multiple of the 128-key tile, d_k = 192 (the FastSpeech2 heads) and d_k = 64."""
+    import math
+    from parakeet_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for (B, T, H, dk, lens) in ((3, 300, 2, 192, [300, 131, 17]), (2, 128, 2, 192, None), (2, 77, 4, 64, [77, 5]), (1, 1400, 2, 192, [1333])):
+        A = H * dk
+        qkv = ops.Split.from_f32((torch.randn(B, T, 3 * A, generator=g) * 1.5).to(cuda))
+        kl = torch.tensor(lens, dtype=torch.int32, device=cuda) if lens else None
+        ctx = ops.fused_attention(qkv, H, key_lens=kl, row_lens=kl).float().cpu().double()
+        x = qkv.float().cpu().double()
+        q, k, v = [x[..., i * A:(i + 1) * A].reshape(B, T, H, dk).transpose(1, 2) for i in range(3)]
+        s = q @ k.transpose(-1, -2) / math.sqrt(dk)
+        keep = torch.ones(B, T, dtype=torch.bool) if lens is None else torch.arange(T)[None, :] < torch.tensor(lens)[:, None]
+        s = s.masked_fill(~keep[:, None, None, :], float("-inf"))
+        ref = (torch.softmax(s, -1).masked_fill(~keep[:, None, None, :], 0.0) @ v).transpose(1, 2).reshape(B, T, A)
+        ref = ref * keep[:, :, None]                                   # rows past an utterance's end are written as zero
+        err = (ctx - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-5, (B, T, H, dk, err)
+        assert ctx[~keep].abs().max().item() == 0 if lens else True
