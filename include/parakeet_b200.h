@@ -255,6 +255,10 @@ int pk_layer_norm(const float* x, const float* gamma, const float* beta, float e
  * keys >= key_lens[b] and the padding columns [keys, ld) get probability 0; output split planes, same layout. */
 int pk_masked_softmax(const float* s, const int32_t* key_lens, int32_t batch, int32_t heads, int32_t rows, int32_t keys,
                       int32_t ld, void* p_hi, void* p_lo, pk_stream_t stream);
+/* paddle.nn.functional.normalize(x, p=2, axis=1, epsilon) on x viewed as (outer, n, inner), norm over the middle axis: the
+ * speaker / tone embedding normalisation of FastSpeech2 (fastspeech2.py:577,581,606,611; axis 1 of a (B, T, D) tone tensor is
+ * TIME in the reference's batched forward).  x, y fp32 contiguous; in place allowed. */
+int pk_l2_normalize(const float* x, int32_t outer, int32_t n, int32_t inner, float eps, float* y, pk_stream_t stream);
 /* Fused scaled-dot-product attention of an FFT block (attention.py:88-131: scores = q k^T / sqrt(d_k), masked_fill(min) ->
  * softmax -> masked_fill(0), p_attn . v, heads merged) in one kernel: scores and probabilities stay in tensor memory.
  *   qkv planes (batch, t, 3 * heads * dk): [q | k | v] of the fused QKV projection, head h in columns h * dk of each third;
@@ -399,6 +403,7 @@ int pk_scalar_conv_wgrad(const float* dhs, const float* track, int32_t batch, in
  * {embedding.py:79,126, attention.py:124, encoder_layer.py:101,108, multi_layer_conv.py:76}, fastspeech2_predictor/
  * {duration_predictor.py:82, variance_predictor.py:73}, tacotron2/decoder.py:144-180 (Postnet). */
 int pk_dropout(const float* x, const void* x_hi, const void* x_lo, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step,
+               const uint32_t* step_dev /* device uint32 added to `step` (NULL: none) - lets a CUDA graph replay draw fresh masks */,
                float* y, void* y_hi, void* y_lo, pk_stream_t stream);
 int pk_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
             int32_t step, float grad_scale, pk_stream_t stream);

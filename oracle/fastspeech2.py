@@ -289,9 +289,28 @@ def postnet(p, xs, n_layers, train_bn=False, new_stats=None, dropout=None, rate=
     return xs
 
 
+def embedding_lookup(table, ids, padding_idx=0):
+    """paddle nn.Embedding(padding_idx): rows of the table, zeros where ids == padding_idx."""
+    e = table[ids]
+    return torch.where((ids == padding_idx).unsqueeze(-1), torch.zeros_like(e), e)
+
+
+def integrate_with_embed(p, name, itype, hs, embs):
+    """_integrate_with_spk_embed / _integrate_with_tone_embed (fastspeech2.py:560-616).  F.normalize is paddle's default
+    (p=2, axis=1, epsilon=1e-12): axis 1 is the feature axis of (B, D) speaker embeddings and of the (T, D) tone embeddings of
+    `inference`, but the TIME axis of the (B, T, D) tone embeddings of the batched `forward` - restated as it is."""
+    n = F.normalize(embs, p=2, dim=1, eps=1e-12)
+    if name == "spk_projection":
+        n = n.unsqueeze(1)                                                    # (B, 1, D)
+    if itype == "add":
+        return hs + linear(p, name, n)
+    return linear(p, name, torch.cat([hs, n.expand(hs.shape[0] if n.dim() == 3 else -1, hs.shape[1], -1)], dim=-1))
+
+
 def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0,
                 return_intermediates=False, train_bn=False, new_stats=None, stop_gradient_from_pitch_predictor=False,
-                stop_gradient_from_energy_predictor=False, dropout=None, rates=None):
+                stop_gradient_from_energy_predictor=False, dropout=None, rates=None, spk_id=None, spembs=None, tone_id=None,
+                tone_per_utterance=False):
     """FastSpeech2._forward (fastspeech2.py:377-466), single speaker, no tones.
     dropout: None (eval / p = 0) or a PhiloxDropout; rates: dict with the reference's constructor keywords (DROPOUT_DEFAULTS).
 
@@ -304,6 +323,17 @@ def fs2_forward(p, cfg, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inf
     R = {**DROPOUT_DEFAULTS, **(rates or {})}
     hs = encoder(p, "encoder.", xs, x_masks, cfg["elayers"], nh, embed=True, dropout=dropout, stack=0,
                  rates=(R["transformer_enc_dropout_rate"], R["transformer_enc_positional_dropout_rate"], R["transformer_enc_attn_dropout_rate"]))
+    if "spk_projection.weight" in p and (spembs is not None or spk_id is not None):                     # fastspeech2.py:395-401
+        emb = spembs if spembs is not None else embedding_lookup(p["spk_embedding_table.weight"], spk_id)
+        hs = integrate_with_embed(p, "spk_projection", cfg.get("spk_embed_integration_type", "add"), hs, emb)
+    if "tone_projection.weight" in p and tone_id is not None:                                            # :403-407
+        emb = embedding_lookup(p["tone_embedding_table.weight"], tone_id)
+        if tone_per_utterance:       # `inference` passes (T,) ids -> (T, D) embeddings: axis 1 is the feature axis there
+            emb = torch.stack([F.normalize(e, p=2, dim=1, eps=1e-12) for e in emb])
+            ty = cfg.get("tone_embed_integration_type", "add")
+            hs = hs + linear(p, "tone_projection", emb) if ty == "add" else linear(p, "tone_projection", torch.cat([hs, emb], dim=-1))
+        else:
+            hs = integrate_with_embed(p, "tone_projection", cfg.get("tone_embed_integration_type", "add"), hs, emb)
     d_masks = make_pad_mask(ilens, xs.shape[1])
     # fastspeech2.py:412-419 (stop_gradient_from_*_predictor -> hs.detach())
     p_outs = variance_predictor(p, "pitch_predictor.", hs.detach() if stop_gradient_from_pitch_predictor else hs,
@@ -443,6 +473,22 @@ def synth_params(seed=1, idim=80, odim=80, cfg=None, target_dur=(2.0, 12.0)):
         p[q + "_mean"] = 0.1 * torch.randn(oc, generator=g)
         p[q + "_variance"] = 1 + 0.1 * torch.rand(oc, generator=g)
     return p
+
+
+def add_speaker_tone_params(p, seed, adim=384, num_speakers=6, spk_embed_dim=256, spk_type="concat", num_tones=7, tone_embed_dim=32,
+                            tone_type="add"):
+    """Speaker / tone tables and projections in the reference's key names and Paddle layouts (Linear [in, out])."""
+    g = torch.Generator().manual_seed(seed + 7000)
+    q = dict(p)
+    q["spk_embedding_table.weight"] = torch.randn(num_speakers, spk_embed_dim, generator=g)
+    i = spk_embed_dim if spk_type == "add" else adim + spk_embed_dim
+    q["spk_projection.weight"] = (torch.rand(i, adim, generator=g) * 2 - 1) * math.sqrt(6.0 / (i + adim))
+    q["spk_projection.bias"] = torch.randn(adim, generator=g) * 0.02
+    q["tone_embedding_table.weight"] = torch.randn(num_tones, tone_embed_dim, generator=g)
+    i = tone_embed_dim if tone_type == "add" else adim + tone_embed_dim
+    q["tone_projection.weight"] = (torch.rand(i, adim, generator=g) * 2 - 1) * math.sqrt(6.0 / (i + adim))
+    q["tone_projection.bias"] = torch.randn(adim, generator=g) * 0.02
+    return q
 
 
 def synth_text(seed, lengths, idim=80):

@@ -93,6 +93,7 @@ def _declare(L):
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],
         "pk_masked_softmax": [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp],
         "pk_transpose_heads": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+        "pk_l2_normalize": [vp, i32, i32, i32, f32, vp, vp],
         "pk_fused_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp],
         "pk_duration_post": [vp, vp, i32, i32, f32, vp, vp, vp],
         "pk_duration_scale": [vp, f32, i64, vp, vp],
@@ -113,7 +114,7 @@ def _declare(L):
         "pk_length_regulate_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
         "pk_scalar_conv_wgrad": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "pk_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
-        "pk_dropout": [vp, vp, vp, i64, f32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp],
+        "pk_dropout": [vp, vp, vp, i64, f32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp],
         "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
         "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],
         "pk_gated_activation": [vp, i64, i32, vp, vp, vp],

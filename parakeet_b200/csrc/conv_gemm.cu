@@ -218,19 +218,28 @@ __device__ __forceinline__ void gemm_epilogue_pair(const GemmKernelArgs& p, floa
   }
 }
 
-struct GemmTile {     // persistent tile schedule: m-tile fastest, then (batch, head), then n-tile, so that the CTAs
-  int m0, n0, bz, hz; // running at the same time share one n-tile of B (the weights stay hot in L2)
-};
+struct GemmTile {     // persistent tile schedule: (batch, head) fastest, then m-tile, then n-tile, so that the CTAs running
+  int m0, n0, bz, hz; // at the same time share one n-tile of B (the weights stay hot in L2) AND the dead tiles of a ragged
+};                    // batch (all utterances' m-tile k for large k) are consecutive indices, i.e. spread evenly over the
+                      // grid-strided CTAs (with m fastest and 148 % tiles_m == 0 some CTAs would own only dead tiles)
 __device__ __forceinline__ GemmTile gemm_tile(int tile, int tiles_m, int zdim, int heads, int block_n) {
   GemmTile t;
-  const int mt = tile % tiles_m;
-  const int r = tile / tiles_m;
-  const int z = r % zdim;
+  const int z = tile % zdim;
+  const int r = tile / zdim;
+  const int mt = r % tiles_m;
   t.m0 = mt * kBlockM;
-  t.n0 = (r / zdim) * block_n;
+  t.n0 = (r / tiles_m) * block_n;
   t.bz = z / heads;
   t.hz = z % heads;
   return t;
+}
+
+// Ragged batches (`lens`): an m-tile that starts at or past its utterance's length holds no live row.  Every role skips it
+// with the same test - no loads, no MMAs, no accumulator hand-over - and the epilogue warps just write its zero rows (the rows
+// are the utterance's own zero padding for the next conv).  On LJSpeech-shaped batches (T ~ U{60..140}, padded to the longest)
+// a third of the m-tiles are dead.
+__device__ __forceinline__ bool gemm_tile_live(const GemmKernelArgs& p, int m0, int bz) {
+  return p.lens == nullptr || m0 < __ldg(p.lens + bz);
 }
 
 template <int BLOCK_N>
@@ -281,6 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       uint32_t it = 0;                                 // running stage counter across tiles
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const GemmTile t = gemm_tile(tile, p.tiles_m, zdim, p.heads, BLOCK_N);
+        if (!gemm_tile_live(p, t.m0, t.bz)) continue;
         const int a_batch = t.bz * p.a_bmul + t.hz * p.a_hmul;
         const int b_batch = t.bz * p.b_bmul + t.hz * p.b_hmul;
         const int a_col = p.a_col0 + t.hz * p.a_colh;
@@ -310,7 +320,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBlockM, BLOCK_N);
       uint32_t it = 0;
       int lt = 0;                                      // tiles processed by this CTA
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const GemmTile t = gemm_tile(tile, p.tiles_m, zdim, p.heads, BLOCK_N);
+        if (!gemm_tile_live(p, t.m0, t.bz)) continue;
         const int buf = lt & 1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
@@ -337,20 +349,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above have read it
         }
         umma_commit(&acc_full[buf]);   // accumulator complete
+        ++lt;
       }
     }
   } else {
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const GemmTile t = gemm_tile(tile, p.tiles_m, zdim, p.heads, BLOCK_N);
       const int buf = lt & 1;
       const int row = t.m0 + quarter * 32 + lane;   // output time step
       const bool row_ok = row < p.m;
       const bool row_live = row_ok && (p.lens == nullptr || row < __ldg(p.lens + t.bz));
       const long long y_off = t.bz * p.y_batch_stride + t.hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
-      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      if (!gemm_tile_live(p, t.m0, t.bz)) {        // dead tile: zero rows, nothing to wait for
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          gemm_epilogue_chunk(p, v, t.n0 + c * 32, row_ok, false, y_off);
+        }
+        continue;
+      }
+      ++lt;
+      mbar_wait(&acc_full[buf], ((lt - 1) >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * Cfg::kTmemCols;
       if (p.epi == PK_EPI_NONE) {
@@ -455,7 +479,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = lds_u32(tmem_slot);
 
-  // tile schedule of the pair: m-pair-tile (256 rows) fastest, then (batch, head), then n-tile; p.tiles_m counts pair tiles
+  // tile schedule of the pair: (batch, head) fastest, then m-pair-tile (256 rows), then n-tile; p.tiles_m counts pair tiles
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------ TMA producer (both CTAs) ------------------------------
@@ -463,12 +487,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       const uint32_t tx_bytes = 2 * ((p.passes == 3) ? Cfg::kStageBytes : (Cfg::kABytes + Cfg::kBBytes));   // both CTAs
       uint32_t it = 0;
       for (int tile = pair_id; tile < p.total_tiles; tile += pair_step) {
-        const int mt = tile % p.tiles_m;
-        const int r = tile / p.tiles_m;
-        const int z = r % zdim;
+        const int z = tile % zdim;
+        const int r = tile / zdim;
+        const int mt = r % p.tiles_m;
         const int m0 = mt * 2 * kBlockM + static_cast<int>(rank) * kBlockM;
-        const int n0 = (r / zdim) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        const int n0 = (r / p.tiles_m) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
         const int bz = z / p.heads, hz = z % p.heads;
+        if (!gemm_tile_live(p, mt * 2 * kBlockM, bz)) continue;      // the PAIR tile (256 rows) is the unit that is skipped
         const int a_batch = bz * p.a_bmul + hz * p.a_hmul;
         const int b_batch = bz * p.b_bmul + hz * p.b_hmul;
         const int a_col = p.a_col0 + hz * p.a_colh;
@@ -499,7 +524,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
       constexpr uint32_t idesc = make_idesc_bf16_f32(2 * kBlockM, BLOCK_N);
       uint32_t it = 0;
       int lt = 0;
-      for (int tile = pair_id; tile < p.total_tiles; tile += pair_step, ++lt) {
+      for (int tile = pair_id; tile < p.total_tiles; tile += pair_step) {
+        if (!gemm_tile_live(p, ((tile / zdim) % p.tiles_m) * 2 * kBlockM, (tile % zdim) / p.heads)) continue;
         const int buf = lt & 1;
         mbar_wait_a(acc_empty + 8 * buf, ((lt >> 1) & 1) ^ 1);
         tcgen05_fence_after();
@@ -526,6 +552,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
           umma_commit_2sm_a(empty_bar + 8 * s);
         }
         umma_commit_2sm_a(acc_full + 8 * buf);
+        ++lt;
       }
     }
   } else {
@@ -533,18 +560,29 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_
     const int quarter = warp & 3;
     const uint32_t acc_empty_l = mapa_shared(acc_empty, 0);
     int lt = 0;
-    for (int tile = pair_id; tile < p.total_tiles; tile += pair_step, ++lt) {
-      const int mt = tile % p.tiles_m;
-      const int r = tile / p.tiles_m;
-      const int z = r % zdim;
-      const int tn0 = (r / zdim) * BLOCK_N;
+    for (int tile = pair_id; tile < p.total_tiles; tile += pair_step) {
+      const int z = tile % zdim;
+      const int r = tile / zdim;
+      const int mt = r % p.tiles_m;
+      const int tn0 = (r / p.tiles_m) * BLOCK_N;
       const int bz = z / p.heads, hz = z % p.heads;
       const int buf = lt & 1;
       const int row = mt * 2 * kBlockM + static_cast<int>(rank) * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.m;
       const bool row_live = row_ok && (p.lens == nullptr || row < __ldg(p.lens + bz));
       const long long y_off = bz * p.y_batch_stride + hz * p.y_head_stride + static_cast<long long>(row) * p.y_ld;
-      mbar_wait_a(acc_full + 8 * buf, (lt >> 1) & 1);
+      if (!gemm_tile_live(p, mt * 2 * kBlockM, bz)) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          gemm_epilogue_chunk(p, v, tn0 + c * 32, row_ok, false, y_off);
+        }
+        continue;
+      }
+      ++lt;
+      mbar_wait_a(acc_full + 8 * buf, ((lt - 1) >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {

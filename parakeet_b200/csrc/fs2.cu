@@ -421,3 +421,40 @@ extern "C" int pk_fs2_loss(const float* before, const float* after, const float*
   count_launch();
   return PK_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// paddle.nn.functional.normalize(x, p=2, axis=1, epsilon=1e-12) on a tensor viewed as (outer, n, inner): y = x / max(||x||_2, eps)
+// with the norm taken over the middle axis.  FastSpeech2 applies it to speaker embeddings (B, D): outer = B, n = D, inner = 1 -
+// and, in the batched forward, to tone embeddings (B, T, D) where axis 1 is TIME (fastspeech2.py:577,581,606,611): outer = B,
+// n = T, inner = D.  One block per (outer, 32-wide slice of inner); tiny tensors, latency bound.
+// ----------------------------------------------------------------------------------------------------------------
+namespace pk {
+__global__ void l2_normalize_kernel(const float* __restrict__ x, int n, int inner, float eps, float* __restrict__ y) {
+  const int o = blockIdx.x, i = blockIdx.y * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5, parts = blockDim.x >> 5;
+  __shared__ float red[8][33];
+  const float* xo = x + static_cast<long long>(o) * n * inner;
+  float acc = 0.f;
+  if (i < inner)
+    for (int k = part; k < n; k += parts) {
+      const float v = xo[static_cast<long long>(k) * inner + i];
+      acc = fmaf(v, v, acc);
+    }
+  red[part][threadIdx.x & 31] = acc;
+  __syncthreads();
+  float tot = 0.f;
+  for (int q = 0; q < parts; ++q) tot += red[q][threadIdx.x & 31];
+  const float inv = 1.f / fmaxf(sqrtf(tot), eps);
+  float* yo = y + static_cast<long long>(o) * n * inner;
+  if (i < inner)
+    for (int k = part; k < n; k += parts) yo[static_cast<long long>(k) * inner + i] = xo[static_cast<long long>(k) * inner + i] * inv;
+}
+}  // namespace pk
+
+extern "C" int pk_l2_normalize(const float* x, int32_t outer, int32_t n, int32_t inner, float eps, float* y, pk_stream_t stream) {
+  PK_CHECK_ARG(x && y && outer > 0 && n > 0 && inner > 0, "bad arguments");
+  dim3 grid(outer, (inner + 31) / 32);
+  pk::l2_normalize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, inner, eps, y);
+  PK_CHECK_CUDA(cudaGetLastError());
+  pk::count_launch();
+  return PK_OK;
+}

@@ -559,11 +559,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __global__ void dropout_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
                                long long n, uint32_t thresh, float scale, uint32_t seed_lo, uint32_t seed_hi, uint32_t site, uint32_t step,
-                               float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+                               const uint32_t* __restrict__ step_dev, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
   const long long blk = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;     // one Philox block = 4 elements
   const long long i0 = blk * 4;
   if (i0 >= n) return;
   uint32_t r[4];
+  if (step_dev) step += __ldg(step_dev);      // device-resident step counter: a captured CUDA graph draws fresh masks on every replay
   philox4x32_10(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, step, seed_lo, seed_hi, r);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -583,7 +584,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, const __nv_bfloat16*
 }  // namespace pk
 
 extern "C" int pk_dropout(const float* x, const void* x_hi, const void* x_lo, int64_t n, float p, uint64_t seed, uint32_t site,
-                          uint32_t step, float* y, void* y_hi, void* y_lo, pk_stream_t stream) {
+                          uint32_t step, const uint32_t* step_dev, float* y, void* y_hi, void* y_lo, pk_stream_t stream) {
   using namespace pk;
   PK_CHECK_ARG((x != nullptr) != (x_hi != nullptr) && (x_hi == nullptr) == (x_lo == nullptr), "give x (fp32) or x_hi + x_lo");
   PK_CHECK_ARG((y || y_hi) && (y_hi == nullptr) == (y_lo == nullptr) && n > 0, "bad outputs / size");
@@ -593,6 +594,6 @@ extern "C" int pk_dropout(const float* x, const void* x_hi, const void* x_lo, in
   const long long blocks4 = (n + 3) / 4;
   dropout_kernel<<<nblk(blocks4, 256), 256, 0, PK_STREAM>>>(x, static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), n,
                                                             thresh, 1.f / (1.f - p), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
-                                                            site, step, y, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
+                                                            site, step, step_dev, y, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
   PK_LAUNCH_DONE()
 }

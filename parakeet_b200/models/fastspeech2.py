@@ -11,9 +11,10 @@ LayerNorm, masked softmax, duration rounding, length regulator) through the pk_*
 There is one device->host copy per call: the B output lengths (sum of durations), needed to size the decoder buffers
 (the reference syncs twice per utterance, nets_utils.py:80 `.tolist()` and length_regulator.py:53 `.numpy()`).
 
-Scope of this round: inference-mode arithmetic (dropout = identity, BatchNorm uses its running statistics) for both
-`inference()` and `forward()`; multi-speaker / tone embeddings, `reduction_factor > 1`, `concat_after` and the
-backward pass are not implemented and raise NotImplementedError.
+Scope: inference-mode arithmetic (dropout = identity, BatchNorm uses its running statistics) for `inference()`,
+`batch_inference()` and `forward()`, including the multi-speaker / tone conditioning of the aishell3 / vctk recipes
+(`spk_id` / `spembs` / `tone_id`, "add" and "concat" integration); the training step lives in training/fs2_step.py
+(single-speaker).  `reduction_factor > 1` and `concat_after` are not implemented and raise NotImplementedError.
 """
 import math
 import os
@@ -102,10 +103,10 @@ class FastSpeech2(Layer):
             seed: int = 0):
         super().__init__(device)
         unsupported = []
-        if spk_embed_dim is not None or num_speakers is not None:
-            unsupported.append("speaker embeddings")
-        if tone_embed_dim is not None or num_tones is not None:
-            unsupported.append("tone embeddings")
+        if spk_embed_dim is not None and spk_embed_integration_type not in ("add", "concat"):
+            unsupported.append(f"spk_embed_integration_type={spk_embed_integration_type}")
+        if tone_embed_dim is not None and tone_embed_integration_type not in ("add", "concat"):
+            unsupported.append(f"tone_embed_integration_type={tone_embed_integration_type}")
         if reduction_factor != 1:
             unsupported.append("reduction_factor > 1")
         if encoder_concat_after or decoder_concat_after:
@@ -149,6 +150,9 @@ class FastSpeech2(Layer):
                         energy=(energy_predictor_layers, energy_predictor_chans, energy_predictor_kernel_size))
         self.stop_gradient_from_pitch_predictor = stop_gradient_from_pitch_predictor
         self.stop_gradient_from_energy_predictor = stop_gradient_from_energy_predictor
+        # multi-speaker / tone conditioning (fastspeech2.py:127-158,190-203): embedding tables + projections
+        self.spk_embed_dim, self.num_speakers, self.spk_embed_integration_type = spk_embed_dim, num_speakers, spk_embed_integration_type
+        self.tone_embed_dim, self.num_tones, self.tone_embed_integration_type = tone_embed_dim, num_tones, tone_embed_integration_type
 
         g = torch.Generator().manual_seed(seed)
         A = adim
@@ -197,6 +201,10 @@ class FastSpeech2(Layer):
                 ln(f"{pre}conv.{i}.2", chans)
             lin(pre + "linear", chans, 1)
 
+        if spk_embed_dim is not None:
+            lin("spk_projection", spk_embed_dim if spk_embed_integration_type == "add" else A + spk_embed_dim, A)
+        if tone_embed_dim is not None:
+            lin("tone_projection", tone_embed_dim if tone_embed_integration_type == "add" else A + tone_embed_dim, A)
         pred("duration_predictor.", *self.cfg["dur"])
         pred("pitch_predictor.", *self.cfg["pitch"])
         conv("pitch_embed.0", A, 1, pitch_embed_kernel_size)
@@ -214,6 +222,12 @@ class FastSpeech2(Layer):
             self._register(q + "bias", torch.zeros(oc))
             self._register(q + "_mean", torch.zeros(oc))
             self._register(q + "_variance", torch.ones(oc))
+        if spk_embed_dim is not None:
+            assert num_speakers, "num_speakers is required with spk_embed_dim"
+            self._register("spk_embedding_table.weight", torch.randn(num_speakers, spk_embed_dim, generator=g))
+        if tone_embed_dim is not None:
+            assert num_tones, "num_tones is required with tone_embed_dim"
+            self._register("tone_embedding_table.weight", torch.randn(num_tones, tone_embed_dim, generator=g))
 
     # ------------------------------------------------------------------------------------------------------------
     # kernel-ready weights (once per weight change)
@@ -224,6 +238,11 @@ class FastSpeech2(Layer):
         p = {k: v.detach().float().cpu() for k, v in self._params.items()}
         dev = self.device
         pk = {}
+        for tag in ("spk", "tone"):
+            if getattr(self, tag + "_embed_dim") is not None:
+                w = p[tag + "_projection.weight"]                          # Paddle Linear [in, out]
+                pk[tag + "_proj"] = dict(w=ops.pack_weight(w.t().contiguous(), dev), b=p[tag + "_projection.bias"].contiguous().to(dev),
+                                         k=w.shape[0])
 
         def dv(t):
             return t.contiguous().to(dev)
@@ -354,15 +373,48 @@ class FastSpeech2(Layer):
     # ------------------------------------------------------------------------------------------------------------
     # _forward (reference fastspeech2.py:377-466)
     # ------------------------------------------------------------------------------------------------------------
-    def _stage_a(self, xs, ilens32, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False):
-        """Encoder, variance predictors, duration rounding, variance embeddings, frame counts: everything whose shapes
-        depend on (B, T) only.  No host synchronisation (CUDA-graph capturable)."""
+    def _embed_ids(self, table_name, ids):
+        """nn.Embedding(padding_idx=0): rows of the table, zeros for id 0 (a gather and a fill: no arithmetic)."""
+        table = self._params[table_name]
+        e = table.index_select(0, ids.reshape(-1)).reshape(tuple(ids.shape) + (table.shape[1],))
+        return e.masked_fill((ids == self.padding_idx).unsqueeze(-1), 0.0)
+
+    def _integrate(self, tag, hs, emb_n, row_lens):
+        """_integrate_with_spk_embed / _integrate_with_tone_embed (fastspeech2.py:560-616) after F.normalize:
+        "add": hs + projection(emb); "concat": projection(concat([hs, emb broadcast over time])).
+        emb_n: (B, D) (speaker) or (B, T, D) / (T, D) (tone).  Returns (hs fp32, hs split planes)."""
+        pk = self._pack()[tag + "_proj"]
+        B, T, A = hs.shape
+        itype = getattr(self, tag + "_embed_integration_type")
+        if emb_n.dim() == 2 and tag == "spk":
+            emb_bt = emb_n.unsqueeze(1)                                     # (B, 1, D)
+        else:
+            emb_bt = emb_n.reshape(-1, T, emb_n.shape[-1])                  # (B or 1, T, D)
+        if itype == "add":
+            proj, _ = ops.conv_gemm(Split.from_f32(emb_bt.contiguous()), pk["w"], n=A, k=pk["k"], bias=pk["b"])
+            out = hs.clone()
+            ops.axpy_(1.0, proj.expand(B, T, A).contiguous(), out)
+            if row_lens is not None:
+                ops.mask_rows_(out, row_lens)
+            return out, Split.from_f32(out)
+        cat = torch.cat([hs, emb_bt.expand(B, T, emb_bt.shape[-1])], dim=-1).contiguous()      # layout only
+        return ops.conv_gemm(Split.from_f32(cat), pk["w"], n=A, k=pk["k"], bias=pk["b"], lens=row_lens, out_f32=True, out_split=True)
+
+    def _stage_a(self, xs, ilens32, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False,
+                 spk_emb=None, tone_emb=None):
+        """Encoder, (speaker / tone integration,) variance predictors, duration rounding, variance embeddings, frame counts:
+        everything whose shapes depend on (B, T) only.  No host synchronisation (CUDA-graph capturable).
+        spk_emb / tone_emb: already normalised embeddings (see _conditioning)."""
         pk = self._pack()
         B, T = xs.shape
         row_lens = ilens32 if independent else None
         # encoder: Embedding(padding_idx=0) + ScaledPositionalEncoding, FFT blocks, after_norm; keys masked by ilens
         x = ops.embed_pe(xs, pk["emb"], None, pk["enc_alpha"], row_lens, self.padding_idx)
         hs, hs_split = self._encoder_stack(x, pk["enc"], pk["enc_norm"], row_lens, ilens32, want_split_out=True)
+        if spk_emb is not None:                                             # fastspeech2.py:395-401
+            hs, hs_split = self._integrate("spk", hs, spk_emb, row_lens)
+        if tone_emb is not None:                                            # :403-407
+            hs, hs_split = self._integrate("tone", hs, tone_emb, row_lens)
         # variance predictors (masked_fill with the pad mask, variance_predictor.py:101-103)
         p_outs = ops.mask_rows_(self._predictor(pk["pitch"], hs_split, row_lens), ilens32)
         e_outs = ops.mask_rows_(self._predictor(pk["energy"], hs_split, row_lens), ilens32)
@@ -395,13 +447,32 @@ class FastSpeech2(Layer):
         after = before if self.postnet_layers == 0 else self._postnet(before, before_split, dec_rows)
         return before, after
 
-    def _forward(self, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False):
+    def _conditioning(self, B, T, spembs=None, spk_id=None, tone_id=None, per_utterance=False):
+        """Speaker / tone embeddings, looked up and L2-normalised as the reference does (F.normalize, axis 1).
+        per_utterance: the single-utterance `inference` path, where tone embeddings are (T, D) and axis 1 is the feature axis;
+        in the batched forward axis 1 of the (B, T, D) tone tensor is TIME (the reference's own behaviour, kept)."""
+        spk_emb = tone_emb = None
+        if self.spk_embed_dim is not None:
+            if spembs is not None:
+                spk_emb = ops.l2_normalize_axis1(spembs.reshape(B, -1).to(self.device))
+            elif spk_id is not None:
+                spk_emb = ops.l2_normalize_axis1(self._embed_ids("spk_embedding_table.weight", spk_id.to(self.device, torch.int64).reshape(B)))
+        if self.tone_embed_dim is not None and tone_id is not None:
+            e = self._embed_ids("tone_embedding_table.weight", tone_id.to(self.device, torch.int64).reshape(B, T))
+            if per_utterance:
+                tone_emb = ops.l2_normalize_axis1(e.reshape(B * T, -1)).reshape(B, T, -1)
+            else:
+                tone_emb = ops.l2_normalize_axis1(e)
+        return spk_emb, tone_emb
+
+    def _forward(self, xs, ilens, olens=None, ds=None, ps=None, es=None, is_inference=False, alpha=1.0, independent=False,
+                 spk_emb=None, tone_emb=None):
         if not xs.is_cuda:
             raise _lib.PkError("FastSpeech2 needs CUDA tensors (no CPU fallback)")
         B = xs.shape[0]
         ilens32 = _i32(ilens.to(xs.device))
         hs2, d_int, lr_lens, d_outs, p_outs, e_outs = self._stage_a(xs.to(torch.int64), ilens32, ds, ps, es, is_inference, alpha,
-                                                                    independent)
+                                                                    independent, spk_emb, tone_emb)
         t_dec = int(lr_lens.max().item())        # the one D2H copy (B integers) that sizes the decoder
         if t_dec == 0:
             empty = torch.zeros(B, 0, self.odim, device=xs.device)
@@ -415,7 +486,7 @@ class FastSpeech2(Layer):
         before, after = self._stage_b(hs2, d_int, t_dec, dec_rows, dec_keys)
         return before, after, d_outs, p_outs, e_outs, lr_lens
 
-    def _infer(self, xs, ilens, alpha=1.0):
+    def _infer(self, xs, ilens, alpha=1.0, spk_emb=None, tone_emb=None):
         """Inference through CUDA graphs (parakeet_b200/graph.py): every utterance is computed as if alone (utterance-local
         padding and key masks), so the decoder length can be rounded up to a bucket of 32 frames - padded rows are inert
         and are sliced off - and the two shape-static halves replay as graphs.  Returns (after, d_outs, frame counts)."""
@@ -425,8 +496,14 @@ class FastSpeech2(Layer):
         xs = xs.to(torch.int64).contiguous()
         ilens32 = _i32(ilens.to(xs.device))
         alpha = float(alpha)
-        fa = lambda x_, l_: self._stage_a(x_, l_, is_inference=True, alpha=alpha, independent=True)
-        hs2, d_int, lr_lens, d_outs, _, _ = self._graphs.run(("a", B, T, alpha), fa, [xs, ilens32])
+        cond = [t for t in (spk_emb, tone_emb) if t is not None]
+        def fa(x_, l_, *c_):
+            c_ = list(c_)
+            se = c_.pop(0) if spk_emb is not None else None
+            te = c_.pop(0) if tone_emb is not None else None
+            return self._stage_a(x_, l_, is_inference=True, alpha=alpha, independent=True, spk_emb=se, tone_emb=te)
+        hs2, d_int, lr_lens, d_outs, _, _ = self._graphs.run(("a", B, T, alpha, spk_emb is not None, tone_emb is not None), fa,
+                                                              [xs, ilens32] + cond)
         t_dec = int(lr_lens.max().item())
         if t_dec == 0:
             return torch.zeros(B, 0, self.odim, device=xs.device), d_outs.clone(), lr_lens.clone()
@@ -440,31 +517,31 @@ class FastSpeech2(Layer):
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, text, text_lengths, speech, speech_lengths, durations, pitch, energy, tone_id=None, spembs=None,
                 spk_id=None):
-        if tone_id is not None or spembs is not None or spk_id is not None:
-            raise NotImplementedError("speaker / tone embeddings are not in this round's scope")
+        spk_emb, tone_emb = self._conditioning(text.shape[0], text.shape[1], spembs, spk_id, tone_id)
         before, after, d_outs, p_outs, e_outs, _ = self._forward(
             text.to(torch.int64), text_lengths.to(torch.int64), speech_lengths.to(torch.int64), durations.to(torch.int64), pitch,
-            energy, is_inference=False)
+            energy, is_inference=False, spk_emb=spk_emb, tone_emb=tone_emb)
         return before, after, d_outs, p_outs, e_outs, speech, speech_lengths.to(torch.int64)
 
     def inference(self, text, speech=None, durations=None, pitch=None, energy=None, alpha: float = 1.0,
                   use_teacher_forcing: bool = False, spembs=None, spk_id=None, tone_id=None):
-        if spembs is not None or spk_id is not None or tone_id is not None:
-            raise NotImplementedError("speaker / tone embeddings are not in this round's scope")
         xs = text.to(torch.int64).unsqueeze(0)
         ilens = torch.tensor([xs.shape[1]], dtype=torch.int64, device=xs.device)
+        spk_emb, tone_emb = self._conditioning(1, xs.shape[1], spembs, spk_id, tone_id, per_utterance=True)
         if use_teacher_forcing:
             _, outs, *_ = self._forward(xs, ilens, None, durations.to(torch.int64).unsqueeze(0), pitch.unsqueeze(0),
-                                        energy.unsqueeze(0), is_inference=False)
+                                        energy.unsqueeze(0), is_inference=False, spk_emb=spk_emb, tone_emb=tone_emb)
         else:
-            outs, _, _ = self._infer(xs, ilens, alpha)
+            outs, _, _ = self._infer(xs, ilens, alpha, spk_emb, tone_emb)
         return outs[0]
 
-    def batch_inference(self, text, text_lengths, alpha: float = 1.0):
+    def batch_inference(self, text, text_lengths, alpha: float = 1.0, spembs=None, spk_id=None, tone_id=None):
         """Batched form of `inference`: padded ids (B, Tmax) + lengths -> (mel (B, Lmax, odim), frame counts (B,) int32,
         durations (B, Tmax)).  Each utterance is computed exactly as if it had been passed to `inference` alone
-        (utterance-local zero padding and key masking); rows past an utterance's own length are zero."""
-        after, d_outs, olens = self._infer(text, text_lengths, alpha)
+        (utterance-local zero padding and key masking, per-utterance normalisation of tone embeddings); rows past an
+        utterance's own length are zero.  spk_id (B,) / spembs (B, D) / tone_id (B, Tmax) as in `forward`."""
+        spk_emb, tone_emb = self._conditioning(text.shape[0], text.shape[1], spembs, spk_id, tone_id, per_utterance=True)
+        after, d_outs, olens = self._infer(text, text_lengths, alpha, spk_emb, tone_emb)
         return after, olens, d_outs
 
 

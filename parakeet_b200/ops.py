@@ -244,6 +244,16 @@ def transpose_heads(src, col0, dk, heads, ld_dst):
     return dst
 
 
+def l2_normalize_axis1(x, eps=1e-12):
+    """paddle F.normalize(x) (p=2, axis=1): (B, D) over D; (B, T, D) over T (the reference's batched tone path)."""
+    x = x.contiguous().float()
+    outer, n = x.shape[0], x.shape[1]
+    inner = x.numel() // (outer * n)
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().pk_l2_normalize(_ptr(x), outer, n, inner, float(eps), _ptr(y), _stream()), "pk_l2_normalize")
+    return y
+
+
 def fused_attention(qkv, heads, key_lens=None, row_lens=None, ctx=None):
     """qkv Split (B, T, 3A) -> ctx Split (B, T, A): softmax(q k^T / sqrt(d_k), key mask) v per head, one kernel
     (pk_fused_attention) after the per-head transpose of v."""
@@ -342,7 +352,7 @@ def axpy_(a, x, y):
     _lib.check(_lib.lib().pk_axpy(float(a), _ptr(x), x.numel(), _ptr(y), _stream()), "pk_axpy")
 
 
-def dropout(x, p, seed, site, step, out_f32=True, out_split=False, inplace=False):
+def dropout(x, p, seed, site, step, out_f32=True, out_split=False, inplace=False, step_dev=None):
     """pk_dropout: x fp32 tensor or Split (any shape, contiguous) -> (y fp32 or None, y Split or None).  p == 0 is not a
     special case here (callers skip the call)."""
     is_split = isinstance(x, Split)
@@ -352,6 +362,6 @@ def dropout(x, p, seed, site, step, out_f32=True, out_split=False, inplace=False
     y = (x if (inplace and not is_split) else torch.empty(ref.shape, dtype=torch.float32, device=ref.device)) if out_f32 else None
     ys = (x if (inplace and is_split) else Split.empty(tuple(ref.shape), ref.device)) if out_split else None
     _lib.check(_lib.lib().pk_dropout(_ptr(None if is_split else x), _ptr(x.hi if is_split else None), _ptr(x.lo if is_split else None), n,
-                                     float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site), int(step), _ptr(y), _ptr(ys.hi if ys else None),
+                                     float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site), int(step), _ptr(step_dev), _ptr(y), _ptr(ys.hi if ys else None),
                                      _ptr(ys.lo if ys else None), _stream()), "pk_dropout")
     return y, ys

@@ -47,12 +47,17 @@ def pack_dev(w):
 class FastSpeech2TrainStep:
     def __init__(self, model: FastSpeech2, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8,
                  stop_gradient_from_pitch_predictor=None, stop_gradient_from_energy_predictor=None, process_group=None,
-                 dropout=True, seed=0):
+                 dropout=True, seed=0, use_graphs=None):
         """dropout: True -> the model's constructor rates (the reference trains in model.train() mode), a dict of the
         reference's rate keywords to override them, or False / None -> every rate 0 (deterministic step, parity tests).
-        seed: base seed of the Philox masks; every rank should pass its own (paddle seeds each process's generator)."""
+        seed: base seed of the Philox masks; every rank should pass its own (paddle seeds each process's generator).
+        use_graphs: replay forward + backward as ONE CUDA graph per batch shape (eager the first time a shape is seen, captured
+        the second, replayed afterwards); None -> env PK_TRAIN_GRAPH (default on).  The step is host-bound otherwise (~700
+        launches of 10-40 us); bucketing samplers repeat shapes, so do synthetic benchmarks."""
         if not model.device.type == "cuda":
             raise _lib.PkError("training needs a CUDA device (no CPU fallback)")
+        if model.spk_embed_dim is not None or model.tone_embed_dim is not None:
+            raise NotImplementedError("the training step covers the single-speaker recipe (speaker / tone conditioning is inference-only)")
         self.m = model
         self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
         self.sg_pitch = model.stop_gradient_from_pitch_predictor if stop_gradient_from_pitch_predictor is None else stop_gradient_from_pitch_predictor
@@ -74,10 +79,11 @@ class FastSpeech2TrainStep:
         else:
             self.rates = {k: 0.0 for k in model.dropout_rates}
         self.seed = int(seed)
-        # EXPERIMENTAL (PK_TRAIN_GRAPH=1, default off, not validated on a GPU yet): forward + backward replayed as a CUDA graph per
-        # batch shape (B, Tmax, Lmax) once a shape repeats (bucketed samplers); the step is host-bound (~600 launches).
+        # completed steps, on the device: the dropout kernels add it to their step argument, so a captured graph of forward +
+        # backward draws new masks on every replay
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._fb_graphs = GraphRunner(max_graphs=16)
-        self.use_graphs = os.environ.get("PK_TRAIN_GRAPH", "0") == "1"
+        self.use_graphs = (os.environ.get("PK_TRAIN_GRAPH", "1") != "0") if use_graphs is None else bool(use_graphs)
         # workspace of the BatchNorm / LayerNorm reductions: 2 floats per channel (pk_batch_norm_train / _bwd)
         widest = max([model.odim, model.adim] + [int(v.shape[0]) for k, v in model._params.items() if k.startswith("postnet.")])
         self.sums = torch.zeros(max(4096, 2 * widest), dtype=torch.float32, device=dev)
@@ -112,7 +118,7 @@ class FastSpeech2TrainStep:
 
     def drop(self, x, p, site, **kw):
         """Forward AND backward: the mask depends only on (seed, step, site, element index)."""
-        return ops.dropout(x, p, self.seed, site, self.step_count + 1, **kw)
+        return ops.dropout(x, p, self.seed, site, 1, step_dev=self.step_dev, **kw)      # step = 1 + completed steps (device counter)
 
     def w_fwd(self, name, kind):
         w = self.P(name)
@@ -524,6 +530,7 @@ class FastSpeech2TrainStep:
                 if k + suffix in opt:
                     buf[o:o + n].copy_(torch.as_tensor(opt[k + suffix]).reshape(-1).to(buf.device, buf.dtype))
         self.step_count = int(opt.get("step_count", state.get("iteration", self.step_count)))
+        self.step_dev.fill_(self.step_count)
         self._packs = {}
 
     def step(self, batch):
@@ -534,5 +541,6 @@ class FastSpeech2TrainStep:
         self.step_count += 1
         _lib.check(_lib.lib().pk_adam(_ptr(self.flat), _ptr(self.gflat), _ptr(self.adam_m), _ptr(self.adam_v), self.flat.numel(),
                                       self.lr, self.b1, self.b2, self.eps, self.step_count, 1.0 / self.world, _stream()), "pk_adam")
+        self.step_dev += 1
         self.m._packed = None
         return losses

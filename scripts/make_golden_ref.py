@@ -103,6 +103,40 @@ def fastspeech2(out):
         out["fs2_loss"] = np.asarray([float(l1), float(dur), float(pitch), float(energy)], dtype=np.float64)
 
 
+def fastspeech2_multispeaker(out):
+    """The aishell3 / vctk shape of the model (conf/default.yaml:76-77: spk_embed_dim 256, concat) plus tone embeddings ("add"):
+    the reference's own inference(spk_id, tone_id) and batched forward(..., spk_id, tone_id) - including its F.normalize(axis=1)
+    over TIME for the batched (B, T, D) tone embeddings."""
+    from oracle import fastspeech2 as ofs
+    from parakeet.models.fastspeech2.fastspeech2 import FastSpeech2
+    for tag, (st, tt) in (("a", ("concat", "add")), ("b", ("add", "concat"))):
+        cfg = dict(ofs.LJSPEECH_MODEL_CFG, num_speakers=6, spk_embed_dim=256, spk_embed_integration_type=st, num_tones=7, tone_embed_dim=32,
+                   tone_embed_integration_type=tt)
+        ref = FastSpeech2(idim=80, odim=80, **cfg)
+        ref.eval()
+        params = ofs.add_speaker_tone_params(ofs.synth_params(1), 1, spk_type=st, tone_type=tt)
+        out[f"fs2ms_{tag}_keys"] = np.asarray(check_keys(ref, params, "FastSpeech2(multi-speaker)"))
+        ref.set_state_dict(params)
+        g = torch.Generator().manual_seed(77)
+        with torch.no_grad():
+            xs, _ = ofs.synth_text(21, [37])
+            tone = torch.randint(0, 7, (37,), generator=g)
+            spk = torch.tensor([4])
+            out[f"fs2ms_{tag}_inf_text"], out[f"fs2ms_{tag}_inf_tone"] = xs[0].numpy(), tone.numpy()
+            # tone "concat" cannot run through the reference's inference(): it expands the (T, D) embeddings with
+            # shape=[-1, T, -1], a -1 in a dimension that does not exist (fastspeech2.py:611-612) - speaker only there
+            out[f"fs2ms_{tag}_inf_mel"] = ref.inference(T(xs[0]), spk_id=T(spk), tone_id=T(tone) if tt == "add" else None).numpy()
+            b = ofs.synth_train_batch(22, [14, 19])
+            tone_b = torch.randint(0, 7, tuple(b["text"].shape), generator=g)
+            spk_b = torch.tensor([1, 5])
+            for k, v in b.items():
+                out[f"fs2ms_{tag}_fwd_{k}"] = v.numpy()
+            out[f"fs2ms_{tag}_fwd_tone"], out[f"fs2ms_{tag}_fwd_spk"] = tone_b.numpy(), spk_b.numpy()
+            res = ref(T(b["text"]), T(b["text_lengths"]), T(b["speech"]), T(b["speech_lengths"]), T(b["durations"]), T(b["pitch"]),
+                      T(b["energy"]), tone_id=T(tone_b), spk_id=T(spk_b))
+            out[f"fs2ms_{tag}_fwd_after"], out[f"fs2ms_{tag}_fwd_d"] = res[1].numpy(), res[2].numpy()
+
+
 def fastspeech2_training(out):
     """The reference model in TRAIN mode (dropout rates set to 0, BatchNorm on batch statistics), its own FastSpeech2Loss, the
     sum of the four losses as in fastspeech2_updater.py:83, torch autograd through the reference's code: the gradients the
@@ -270,6 +304,7 @@ def main():
         small, models = {}, {}
         small_pieces(small)
         fastspeech2(models)
+        fastspeech2_multispeaker(models)
         fastspeech2_training(models)
         parallel_wavegan(models)
         pwg_discriminator(models)

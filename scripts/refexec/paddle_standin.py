@@ -48,7 +48,9 @@ class Tensor(torch.Tensor):
             return torch.max(self)
         return torch.max(self, dim=kw.get("dim", axis), keepdim=keepdim).values
 
-    def expand(self, *shape):
+    def expand(self, *shape, **kw):                      # paddle: Tensor.expand(shape=[...]) (-1 keeps a dimension)
+        if "shape" in kw:
+            shape = kw["shape"]
         if len(shape) == 1 and isinstance(shape[0], (list, tuple)):
             shape = shape[0]
         return torch.Tensor.expand(self, *shape)

@@ -64,3 +64,37 @@ def test_waveflow_cuda_vs_executed_reference(cuda, g):
     mel2, z2 = torch.from_numpy(g["wf2_mel"]).to(cuda), torch.from_numpy(g["wf2_z"]).to(cuda)
     out2 = wf.infer(mel2, z=z2)
     assert tuple(out2.shape) == g["wf2_x"].shape and rel_err(out2, torch.from_numpy(g["wf2_x"])) < TOL
+
+
+def test_fs2_multispeaker_tone_cuda_vs_executed_reference(cuda, g):
+    """FastSpeech2 with speaker + tone conditioning (both integration types) on the CUDA path against the vectors the
+    reference's own code produced: inference(spk_id, tone_id), batched forward, and batch_inference == per-utterance inference."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    for tag, (st, tt) in (("a", ("concat", "add")), ("b", ("add", "concat"))):
+        p = ofs.add_speaker_tone_params(ofs.synth_params(1), 1, spk_type=st, tone_type=tt)
+        m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, num_speakers=6, spk_embed_dim=256, spk_embed_integration_type=st, num_tones=7,
+                        tone_embed_dim=32, tone_embed_integration_type=tt, device=cuda)
+        assert sorted(m.state_dict()) == list(g[f"fs2ms_{tag}_keys"])
+        m.set_state_dict(p)
+        text, tone = torch.from_numpy(g[f"fs2ms_{tag}_inf_text"]).to(cuda), torch.from_numpy(g[f"fs2ms_{tag}_inf_tone"]).to(cuda)
+        spk = torch.tensor([4], device=cuda)
+        mel = m.inference(text, spk_id=spk, tone_id=tone if tt == "add" else None)
+        ref = torch.from_numpy(g[f"fs2ms_{tag}_inf_mel"])
+        assert tuple(mel.shape) == tuple(ref.shape) and rel_err(mel, ref) < TOL
+        b = {k: torch.from_numpy(g[f"fs2ms_{tag}_fwd_{k}"]).to(cuda) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+        o = m(b["text"], b["text_lengths"], b["speech"], b["speech_lengths"], b["durations"], b["pitch"], b["energy"],
+              tone_id=torch.from_numpy(g[f"fs2ms_{tag}_fwd_tone"]).to(cuda), spk_id=torch.from_numpy(g[f"fs2ms_{tag}_fwd_spk"]).to(cuda))
+        assert rel_err(o[1], torch.from_numpy(g[f"fs2ms_{tag}_fwd_after"])) < TOL
+        assert rel_err(o[2], torch.from_numpy(g[f"fs2ms_{tag}_fwd_d"])) < TOL
+        if tt == "add":      # ragged batch == the utterances one by one (per-utterance tone normalisation)
+            lengths = [37, 21]
+            ids = torch.zeros(2, 37, dtype=torch.int64, device=cuda)
+            tones = torch.zeros(2, 37, dtype=torch.int64, device=cuda)
+            ids[0], tones[0] = text, tone
+            ids[1, :21], tones[1, :21] = text[5:26], tone[3:24]
+            spk2 = torch.tensor([4, 2], device=cuda)
+            melb, olens, _ = m.batch_inference(ids, torch.tensor(lengths, device=cuda), spk_id=spk2, tone_id=tones)
+            assert rel_err(melb[0, :int(olens[0])], ref) < TOL
+            one = m.inference(ids[1, :21], spk_id=spk2[1:], tone_id=tones[1, :21])
+            assert one.shape[0] == int(olens[1]) and rel_err(melb[1, :int(olens[1])], one) < 1e-4

@@ -297,3 +297,30 @@ def test_fs2_training_step_with_the_shipped_dropout_rates_vs_oracle(cuda):
     first = float(ts.step(batch).sum())                                    # step 1 (same masks as above), then step 2: new masks
     second_fb = [float(v) for v in ts.forward_backward(batch)]
     assert np.allclose(first, sum(ref), rtol=1e-3) and abs(sum(second_fb) - first) > 1e-3
+
+
+def test_fs2_training_graph_replay_matches_eager(cuda):
+    """forward + backward replayed as a CUDA graph (third step on) against the eager step, with dropout on: the device-side
+    step counter must give every replay fresh masks (same as eager), losses and parameters agree to reduction-order noise."""
+    from oracle import fastspeech2 as ofs
+    from parakeet_b200.models import FastSpeech2
+    from parakeet_b200.training import FastSpeech2TrainStep
+    params = ofs.synth_params(1)
+    batch = ofs.synth_train_batch(71, [20, 33, 27])
+    rates = dict(ofs.YAML_DROPOUT)
+    runs = []
+    for graphs in (False, True):
+        m = FastSpeech2(80, 80, **ofs.LJSPEECH_MODEL_CFG, stop_gradient_from_pitch_predictor=True, device=cuda, **rates)
+        m.set_state_dict(params)
+        ts = FastSpeech2TrainStep(m, learning_rate=2e-5, dropout=True, seed=5, use_graphs=graphs)
+        losses = [float(ts.step(batch).sum()) for _ in range(5)]
+        runs.append((losses, {k: v.detach().double().cpu().clone() for k, v in m.state_dict().items()}, ts))
+    assert runs[1][2]._fb_graphs.replays >= 3 and runs[0][2]._fb_graphs.replays == 0
+    assert np.allclose(runs[0][0], runs[1][0], rtol=2e-4), (runs[0][0], runs[1][0])
+    assert len(set(round(v, 4) for v in runs[1][0])) == 5                  # five different mask sets -> five different losses
+    for k, v in runs[0][1].items():
+        init = params[k].double()
+        if (v - init).abs().max().item() < 2e-5 or k.endswith("self_attn.linear_k.bias"):
+            continue                                                        # zero-gradient tensors (see the trajectory test)
+        d = (runs[1][1][k] - v).norm().item() / max((v - init).norm().item(), 1e-12)
+        assert d < 5e-2, (k, d)

@@ -145,3 +145,25 @@ def test_pwg_discriminator_equals_executed_reference(g):
     with torch.no_grad():
         y = opwg.discriminator_forward(dp, torch.from_numpy(g["pwgd_x"]))
     assert rel_err(y, torch.from_numpy(g["pwgd_y"])) < TOL
+
+
+def test_multispeaker_tone_oracle_equals_executed_reference(g):
+    """aishell3 / vctk shape (speaker table + projection, concat or add) with tone embeddings: the reference's own
+    inference(spk_id, tone_id) and batched forward(..., tone_id, spk_id) against the oracle, both integration types."""
+    from oracle import fastspeech2 as ofs
+    for tag, (st, tt) in (("a", ("concat", "add")), ("b", ("add", "concat"))):
+        p = ofs.add_speaker_tone_params(ofs.synth_params(1), 1, spk_type=st, tone_type=tt)
+        assert sorted(p) == list(g[f"fs2ms_{tag}_keys"])
+        cfg = dict(spk_embed_integration_type=st, tone_embed_integration_type=tt)
+        text, tone = torch.from_numpy(g[f"fs2ms_{tag}_inf_text"]), torch.from_numpy(g[f"fs2ms_{tag}_inf_tone"])
+        with torch.no_grad():
+            out = ofs.fs2_forward(p, cfg, text.unsqueeze(0), torch.tensor([text.shape[0]]), is_inference=True, spk_id=torch.tensor([4]),
+                                  tone_id=tone.unsqueeze(0) if tt == "add" else None, tone_per_utterance=True)
+        ref = torch.from_numpy(g[f"fs2ms_{tag}_inf_mel"])
+        assert out[1][0].shape == ref.shape and rel_err(out[1][0], ref) < TOL
+        b = {k: torch.from_numpy(g[f"fs2ms_{tag}_fwd_{k}"]) for k in ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")}
+        with torch.no_grad():
+            fw = ofs.fs2_forward(p, cfg, b["text"], b["text_lengths"], b["speech_lengths"], b["durations"], b["pitch"], b["energy"],
+                                 spk_id=torch.from_numpy(g[f"fs2ms_{tag}_fwd_spk"]), tone_id=torch.from_numpy(g[f"fs2ms_{tag}_fwd_tone"]))
+        assert rel_err(fw[1], torch.from_numpy(g[f"fs2ms_{tag}_fwd_after"])) < TOL
+        assert rel_err(fw[2], torch.from_numpy(g[f"fs2ms_{tag}_fwd_d"])) < TOL
