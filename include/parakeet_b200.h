@@ -408,6 +408,47 @@ int pk_dropout(const float* x, const void* x_hi, const void* x_lo, int64_t n, fl
 int pk_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
             int32_t step, float grad_scale, pk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Parallel WaveGAN training step (reference: PWGUpdater.update_core, models/parallel_wavegan/parallel_wavegan_updater.py:76-153;
+ * generator :445-472, PWGDiscriminator :554-614, MultiResolutionSTFTLoss modules/stft_loss.py:163-219).  Every Conv1D forward /
+ * data gradient / weight gradient and the DFTs run through pk_conv_gemm; these are the element-wise pieces in between.
+ * Shapes are channels-last (rows = batch * t) fp32 unless noted.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* z = tanh(h[:, :c]) * sigmoid(h[:, c:])  (ResidualBlock :307-310); h (rows, 2c); outputs fp32 and/or split planes (rows, c). */
+int pk_gate_fwd(const float* h, int64_t rows, int32_t c, float* z, void* z_hi, void* z_lo, pk_stream_t stream);
+int pk_gate_bwd(const float* h, const float* dz, int64_t rows, int32_t c, float* dh, pk_stream_t stream);
+/* nn.LeakyReLU(negative_slope) forward (fp32 and/or split planes out) and backward (x = the pre-activation). */
+int pk_leaky_relu(const float* x, int64_t n, float slope, float* y, void* y_hi, void* y_lo, pk_stream_t stream);
+int pk_leaky_relu_bwd(const float* x, const float* dy, int64_t n, float slope, float* dx, pk_stream_t stream);
+/* nn.utils.weight_norm (dim 0): w[r, :] = g[r] * v[r, :] / ||v[r, :]||; backward: dg, dv from dw.  v (rows, inner). */
+int pk_weight_norm_fwd(const float* v, const float* g, int32_t rows, int32_t inner, float* w, float* norm, pk_stream_t stream);
+int pk_weight_norm_bwd(const float* v, const float* g, const float* dw, int32_t rows, int32_t inner, float* dg, float* dv, pk_stream_t stream);
+/* MSELoss against a constant over x[i * ld + col], i < n: acc[0] += sum (x - target)^2 (device double); dx (or NULL) = coef * (x - target). */
+int pk_mse_const(const float* x, int64_t n, int32_t ld, int32_t col, float target, double* acc, float* dx, float coef, pk_stream_t stream);
+/* acc[0] += sum x^2 (device double): the global gradient norm of ClipGradByGlobalNorm. */
+int pk_sq_sum(const float* x, int64_t n, double* acc, pk_stream_t stream);
+/* pk_adam with ClipGradByGlobalNorm folded in: g <- g * clip / max(sqrt(*sqnorm), clip) (sqnorm NULL or clip <= 0: no clipping). */
+int pk_adam_clip(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int32_t step, const double* sqnorm, float clip_norm, pk_stream_t stream);
+/* generator residual / skip update (:311-315, :466-468): so (rows, 128) = [skip | out]; skips (=|+=) skip; xo = (out + x) * sqrt(1/2)
+ * as fp32 and split planes; and its backward: dso = [dskips | dxo * sqrt(1/2)], dx_res = dxo * sqrt(1/2). */
+int pk_pwg_res_update(const float* so, const float* x, int64_t rows, float* skips, int32_t init, float* xo, void* xo_hi, void* xo_lo,
+                      pk_stream_t stream);
+int pk_pwg_res_update_bwd(const float* dskips, const float* dxo, int64_t rows, float* dso, float* dx_res, pk_stream_t stream);
+/* one upsampling stage (Stretch2D nearest x s + Conv2D FIR of 2s+1 taps, zero pad s; :48-63,119-138) on x (rows, tin) -> (rows, tin*s),
+ * and its backward: dx (rows, tin) and/or dfir[2s+1] (device double, accumulated). */
+int pk_up_stage_fwd(const float* x, const float* fir, int64_t rows, int32_t tin, int32_t s, float* y, pk_stream_t stream);
+int pk_up_stage_bwd(const float* x, const float* dy, const float* fir, int64_t rows, int32_t tin, int32_t s, float* dx, double* dfir,
+                    pk_stream_t stream);
+/* gradient of weight * (spectral convergence + log STFT magnitude) of ONE resolution (stft_loss.py:20-161) w.r.t. re / im of the
+ * generated signal's STFT: x / y re, im (batch, bins, frames) from pk_stft; sums = the device fp32[3] of pk_spectral_loss_sums;
+ * g (batch * frames, 2 * bins_p) row-major [re | im] (padding columns are not written: zero them once). */
+int pk_stft_loss_grad(const float* xre, const float* xim, const float* yre, const float* yim, int32_t batch, int32_t bins, int32_t frames,
+                      int32_t bins_p, const float* sums, float weight, float* g, pk_stream_t stream);
+/* adjoint of framing (centre, reflect padding, window): dx[b, reflect(f * hop + k - n_fft / 2)] += frames_grad[b, f, k] * window[k]. */
+int pk_frames_overlap_add(const float* frames_grad, const float* window, int32_t batch, int32_t frames, int32_t n_fft, int32_t hop,
+                          int32_t t, float* dx, pk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

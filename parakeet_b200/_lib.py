@@ -114,6 +114,21 @@ def _declare(L):
         "pk_length_regulate_bwd": [vp, vp, i32, i32, i32, i32, vp, vp],
         "pk_scalar_conv_wgrad": [vp, vp, i32, i32, i32, i32, vp, vp, vp],
         "pk_adam": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp],
+        "pk_gate_fwd": [vp, i64, i32, vp, vp, vp, vp],
+        "pk_gate_bwd": [vp, vp, i64, i32, vp, vp],
+        "pk_leaky_relu": [vp, i64, f32, vp, vp, vp, vp],
+        "pk_leaky_relu_bwd": [vp, vp, i64, f32, vp, vp],
+        "pk_weight_norm_fwd": [vp, vp, i32, i32, vp, vp, vp],
+        "pk_weight_norm_bwd": [vp, vp, vp, i32, i32, vp, vp, vp],
+        "pk_mse_const": [vp, i64, i32, i32, f32, vp, vp, f32, vp],
+        "pk_sq_sum": [vp, i64, vp, vp],
+        "pk_adam_clip": [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp, f32, vp],
+        "pk_pwg_res_update": [vp, vp, i64, vp, i32, vp, vp, vp, vp],
+        "pk_pwg_res_update_bwd": [vp, vp, i64, vp, vp, vp],
+        "pk_up_stage_fwd": [vp, vp, i64, i32, i32, vp, vp],
+        "pk_up_stage_bwd": [vp, vp, vp, i64, i32, i32, vp, vp, vp],
+        "pk_stft_loss_grad": [vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, vp, vp],
+        "pk_frames_overlap_add": [vp, vp, i32, i32, i32, i32, i32, vp, vp],
         "pk_dropout": [vp, vp, vp, i64, f32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp],
         "pk_waveflow_upsample": [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp],
         "pk_waveflow_input_proj": [vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp],

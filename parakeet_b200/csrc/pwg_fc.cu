@@ -55,6 +55,8 @@ struct FcLayerArgs {
   float k_a, k_g;
   float* skip;
   int skip_init;
+  const __nv_bfloat16* x_hi;    // layer input planes (re-read for the residual add when kResidMma == false)
+  const __nv_bfloat16* x_lo;
   __nv_bfloat16* y_hi;
   __nv_bfloat16* y_lo;
   unsigned long long* prof;
@@ -112,7 +114,10 @@ struct FcTileIter {   // 256-sample tiles of the pair; this CTA owns rows [m0 + 
   }
 };
 
-template <bool kProf>
+// kResidMma: the residual add `+ x` as a tensor-core pass (x [0 | I] into the GEMM2 accumulator, 8 MMAs per tile, no global
+// loads) or, when false, in the out-store warps from global memory (the rows were just streamed by TMA, so they hit L2):
+// 8 fewer shared-memory-fed MMAs against 16 LDG.128 per thread and tile.  PK_PWG_RESID=ldg selects the latter (experiment).
+template <bool kProf, bool kResidMma>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwgThreads, 1)
 pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_u,
                     const __grid_constant__ CUtensorMap tm_p,          // 4-D maps: both planes of a tile in one TMA box
@@ -274,7 +279,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             const int wj = j == 0 ? 0 : j == 1 ? 2 : 1;
             mma_chunk(d, st, w1 + wj * 2 * kFcWTile, 4, j == 0);
           }
-          if (j == kFcG1Chunks - 1) {
+          if (kResidMma && j == kFcG1Chunks - 1) {
             // residual pass: acc2(i) = [0 | x_hi + x_lo] from the centre-tap tiles of both CTAs
             PK_TICK(2)
             mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
@@ -298,6 +303,10 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         PK_TICK(2)
         mbar_wait_a(z_full + 8 * buf, (i >> 1) & 1);   // the gate warps of both CTAs wrote z over acc1(buf), tcgen05.wait::st done
         PK_TICK(3)
+        if (!kResidMma) {
+          mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+          PK_TICK(4)
+        }
         tcgen05_fence_after();
         // A from tensor memory: z_hi / z_lo of channels [32 h, 32 h + 32) sit in columns 32 h + [0, 16) / 32 h + [16, 32) of
         // acc1(buf), one 32-bit column per channel pair, so K-step k (channels 16 k ..) starts at column 32 (k / 2) + 8 (k % 2)
@@ -307,7 +316,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         for (int k = 0; k < 4; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
           const uint32_t a_hi = za + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
-          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, 1);           // on top of the residual pass
+          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, kResidMma || k != 0);   // on top of the residual pass (if any)
           umma_bf16_2sm_ts(d2, a_lo, b_hi + koff, idesc, 1);
           umma_bf16_2sm_ts(d2, a_hi, b_lo + koff, idesc, 1);
         }
@@ -442,6 +451,15 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         const int trow = m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
         const long long row_off = (static_cast<long long>(b) * p.t + trow) * 64;
         const bool live = trow < len;
+        uint4 xh[4], xl[4];                       // kResidMma == false: 32 channels of this row's input, both planes
+        auto load_x = [&](int pass) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            xh[q] = live ? __ldg(reinterpret_cast<const uint4*>(p.x_hi + row_off + pass * 32) + q) : make_uint4(0, 0, 0, 0);
+            xl[q] = live ? __ldg(reinterpret_cast<const uint4*>(p.x_lo + row_off + pass * 32) + q) : make_uint4(0, 0, 0, 0);
+          }
+        };
+        if (!kResidMma) load_x(0);                // issued before the wait: the latency hides behind GEMM2 of this tile
         PK_TICK(6)
         mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
         PK_TICK(0)
@@ -457,6 +475,16 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l + 8 * buf);
+          }
+          if (!kResidMma) {
+            const uint32_t* wh = reinterpret_cast<const uint32_t*>(xh);
+            const uint32_t* wl = reinterpret_cast<const uint32_t*>(xl);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              v[2 * e] += __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+              v[2 * e + 1] += __uint_as_float(wh[e] & 0xffff0000u) + __uint_as_float(wl[e] & 0xffff0000u);
+            }
+            if (pass == 0) load_x(1);
           }
           uint32_t oh[16], ol[16];
 #pragma unroll
@@ -522,8 +550,10 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   if ((rc = encode_tmap_bf16_3d(&tw2_lo, a->w2_lo, 64, 128, 1, 64, 0, 64))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
     attr_set = true;
   }
   FcLayerArgs p;
@@ -538,15 +568,20 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
     p.gate_c[64 + i] = -kLog2e * a->bias1[64 + i];
     p.out_b[i] = a->bias2[64 + i];
   }
+  p.x_hi = static_cast<const __nv_bfloat16*>(a->x_hi); p.x_lo = static_cast<const __nv_bfloat16*>(a->x_lo);
   p.y_hi = static_cast<__nv_bfloat16*>(a->y_hi); p.y_lo = static_cast<__nv_bfloat16*>(a->y_lo);
   p.prof = static_cast<unsigned long long*>(a->prof);
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int pair_tiles = ((a->t + 255) / 256) * a->batch;
   const int grid = 2 * std::min(pair_tiles, sm_count() / 2);
-  if (p.prof != nullptr)
-    pwg_layer_fc_kernel<true><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
-  else
-    pwg_layer_fc_kernel<false><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p);
+  static const bool resid_mma = [] { const char* e = getenv("PK_PWG_RESID"); return !(e && strcmp(e, "ldg") == 0); }();
+#define PK_FC_LAUNCH(PROF, RES) pwg_layer_fc_kernel<PROF, RES><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p)
+  if (p.prof != nullptr) {
+    if (resid_mma) PK_FC_LAUNCH(true, true); else PK_FC_LAUNCH(true, false);
+  } else {
+    if (resid_mma) PK_FC_LAUNCH(false, true); else PK_FC_LAUNCH(false, false);
+  }
+#undef PK_FC_LAUNCH
   PK_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return PK_OK;

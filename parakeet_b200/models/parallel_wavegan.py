@@ -375,6 +375,65 @@ class PWGGenerator(Layer):
         return self.forward(x, c).squeeze(0).transpose(0, 1)
 
 
+class PWGDiscriminator(Layer):
+    """Convolutional discriminator of Parallel WaveGAN (reference parallel_wavegan.py:523-627): layers - 1 x [Conv1D(k, dilation
+    d_i, 'same' zero padding) + LeakyReLU] + Conv1D(k), weight norm on every conv.  Same constructor keywords and state-dict keys
+    (`conv_layers.{2 i}.{weight_g, weight_v, bias}`: the Sequential alternates convs and activations).  `forward` and the
+    training step (training/pwg_step.py) run every conv through pk_conv_gemm."""
+
+    def __init__(self, in_channels: int = 1, out_channels: int = 1, kernel_size: int = 3, layers: int = 10, conv_channels: int = 64,
+                 dilation_factor: int = 1, nonlinear_activation: str = "LeakyReLU",
+                 nonlinear_activation_params: Dict[str, Any] = {"negative_slope": 0.2}, bias: bool = True, use_weight_norm: bool = True,
+                 device=None, seed: int = 0):
+        super().__init__(device)
+        assert kernel_size % 2 == 1 and dilation_factor > 0
+        if nonlinear_activation != "LeakyReLU" or in_channels != 1 or out_channels != 1:
+            raise NotImplementedError("LeakyReLU, 1 input / output channel (the shipped configs)")
+        self.layers, self.kernel_size, self.conv_channels = layers, kernel_size, conv_channels
+        self.slope = float(nonlinear_activation_params.get("negative_slope", 0.01))
+        self.dilations = [1 if i == 0 else (i if dilation_factor == 1 else dilation_factor ** i) for i in range(layers - 1)] + [1]
+        self._weight_norm = False
+        g = torch.Generator().manual_seed(seed)
+        cin = in_channels
+        for i in range(layers):
+            cout = out_channels if i == layers - 1 else conv_channels
+            bound = 1.0 / math.sqrt(cin * kernel_size)
+            self._register(f"conv_layers.{2 * i}.weight", (torch.rand(cout, cin, kernel_size, generator=g) * 2 - 1) * bound)
+            if bias:
+                self._register(f"conv_layers.{2 * i}.bias", (torch.rand(cout, generator=g) * 2 - 1) * bound)
+            cin = conv_channels
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    apply_weight_norm = PWGGenerator.apply_weight_norm
+    remove_weight_norm = PWGGenerator.remove_weight_norm
+    _folded = PWGGenerator._folded
+
+    def forward(self, x):
+        """(N, 1, T) audio -> (N, 1, T) logits."""
+        if not x.is_cuda:
+            raise _lib.PkError("PWGDiscriminator.forward needs CUDA tensors (no CPU fallback)")
+        w = {k: v.float() for k, v in self._folded().items()}
+        B, _, T = x.shape
+        x8 = torch.zeros(B, T, 8, dtype=torch.float32, device=x.device)
+        x8[:, :, 0] = x[:, 0]
+        h = Split.from_f32(x8)
+        L = _lib.lib()
+        for i in range(self.layers):
+            name = f"conv_layers.{2 * i}"
+            wt = w[name + ".weight"]
+            cout, cin, k = wt.shape
+            cin_p = h.hi.shape[-1]
+            wp = torch.zeros(cout, cin_p, k, dtype=torch.float32, device=x.device)
+            wp[:, :cin] = wt
+            y, _ = ops.conv_gemm(h, ops.pack_weight(wp, x.device), n=cout, k=cin_p, taps=k, dil=self.dilations[i], bias=w.get(name + ".bias"))
+            if i < self.layers - 1:
+                a = Split.empty(tuple(y.shape), y.device)
+                _lib.check(L.pk_leaky_relu(_ptr(y), y.numel(), self.slope, None, _ptr(a.hi), _ptr(a.lo), _stream()), "pk_leaky_relu")
+                h = a
+        return y.transpose(1, 2).contiguous()
+
+
 class PWGInference(Layer):
     """reference parallel_wavegan.py:766-775."""
 
