@@ -507,6 +507,34 @@ def main():
             wf_ms = e0.elapsed_time(e1) / 3
             out["extra"]["waveflow_b16_c64"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
                                                 "note": "cfg4; one CUDA graph per call (fused GEMM epilogues)"}
+            # Parallel WaveGAN training step (the workload of the reference's own benchmark harness, tests/benchmark/PWGAN/
+            # run_benchmark.sh: batch 6, batch_max_steps 25 500, metric sequences/s), past discriminator_train_start_steps: generator
+            # step with the adversarial term + discriminator step
+            from parakeet_b200.models import PWGDiscriminator
+            from parakeet_b200.training import PWGTrainStep
+            gen_t = PWGGenerator(layers=30, stacks=3, residual_channels=64, gate_channels=128, skip_channels=64, aux_channels=80,
+                                 aux_context_window=2, upsample_scales=[4, 5, 3, 5], use_weight_norm=True, device=dev, seed=5)
+            dis_t = PWGDiscriminator(device=dev, seed=6)
+            pts = PWGTrainStep(gen_t, dis_t, discriminator_train_start_steps=0)
+            pts.iteration = 1
+            gt = torch.Generator().manual_seed(9)
+            bt, ft = 6, 85
+            wav_t = (torch.randn(bt, 1, ft * HOP, generator=gt) * 0.3).to(dev)
+            mel_t = torch.randn(bt, 80, ft + 4, generator=gt).to(dev)
+            for _ in range(2):
+                lt = pts.update_core((wav_t, mel_t))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                lt = pts.update_core((wav_t, mel_t))
+            e1.record()
+            torch.cuda.synchronize()
+            pt_ms = e0.elapsed_time(e1) / 5
+            out["extra"]["pwg_train_step_b6"] = {"sequences_per_s": bt / (pt_ms * 1e-3), "samples_per_s": bt * ft * HOP / (pt_ms * 1e-3),
+                                                 "ms_per_step": pt_ms, "generator_loss": float(lt["generator_loss"]),
+                                                 "discriminator_loss": float(lt["discriminator_loss"]),
+                                                 "note": "PWGUpdater.update_core: G step (MR-STFT + adversarial) + D step, batch 6 x 25 500 samples, "
+                                                         "unfused training formulation (separate tcgen05 GEMMs + element-wise kernels)"}
         except Exception as ex:  # extras must never break the headline line
             out.setdefault("extra", {})["error"] = repr(ex)
     if not args.no_extra and world == 1:

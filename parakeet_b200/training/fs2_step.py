@@ -24,6 +24,7 @@ from .. import _lib, ops
 from ..models.fastspeech2 import FastSpeech2, _i32
 from ..ops import Split, _ptr, _stream
 from ..graph import GraphRunner
+from . import wgrad
 from .flat import FlatBuffers
 
 BUFFERS = ("_mean", "_variance")
@@ -156,27 +157,23 @@ class FastSpeech2TrainStep:
         return dx
 
     def wgrad(self, x, dys, wname, kind, cin, cout, taps):
+        """dW = X^T dY over the flattened (batch, time) axis, split-K (training/wgrad.py)."""
         B, T = x.hi.shape[0], x.hi.shape[1]
-        Tp = _ceil64(T)
-        KK = B * Tp
         dev = x.hi.device
-        dyt = Split.zeros((cout, KK), dev)
+        Tp, S, ks, KKp = wgrad.plan(B, T, cout, cin)
+        dyt = Split.zeros((cout, KKp), dev)
         ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * dys.hi.shape[2], ld_src=dys.hi.shape[2], c0=0, cols=cout, shift=0,
-                             r_out=T, dst=dyt, dst_zstride=Tp, ld_dst=KK)
+                             r_out=T, dst=dyt, dst_zstride=Tp, ld_dst=KKp)
         pad = (taps - 1) // 2
         tmp = torch.empty(taps, cout, cin, dtype=torch.float32, device=dev) if kind == "conv" else None
         for tap in range(taps):
-            xt = Split.zeros((cin, KK), dev)
+            xt = Split.zeros((cin, KKp), dev)
             ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin, shift=tap - pad,
-                                 r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KK)
-            sx = dict(rows=cin, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
-            sy = dict(rows=cout, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
+                                 r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KKp)
             if kind == "lin":    # Paddle Linear weight [in, out]
-                ops.batched_matmul_nt(xt, dyt, batch=1, heads=1, m=cin, n=cout, k=KK, a_spec=sx, b_spec=sy, y_f32=self.grads[wname],
-                                      y_batch_stride=0, y_head_stride=0, y_ld=cout)
+                wgrad.nt_splitk(xt, dyt, cin, cout, S, ks, KKp, out=self.grads[wname])
             else:                # Conv1D weight [out, in, k]
-                ops.batched_matmul_nt(dyt, xt, batch=1, heads=1, m=cout, n=cin, k=KK, a_spec=sy, b_spec=sx, y_f32=tmp[tap],
-                                      y_batch_stride=0, y_head_stride=0, y_ld=cin)
+                wgrad.nt_splitk(dyt, xt, cout, cin, S, ks, KKp, out=tmp[tap])
         if kind == "conv":
             self.grads[wname].copy_(tmp.permute(1, 2, 0))
 
@@ -312,16 +309,12 @@ class FastSpeech2TrainStep:
             wq_b = self._pack(("b", q + "qkv"), lambda: pack_dev(torch.cat([self.P(q + "self_attn.linear_q.weight"), self.P(q + "self_attn.linear_k.weight"),
                                                                            self.P(q + "self_attn.linear_v.weight")], dim=1).contiguous()))
             dh1, _ = ops.conv_gemm(dqs, wq_b, n=A, k=ld)
-            gw = torch.empty(A, ld, dtype=torch.float32, device=dev)
-            KK = B * Tp
-            xt = Split.zeros((A, KK), dev)
-            ops.transpose_planes(c["h1"], z=B, rows=T, src_zstride=T * A, ld_src=A, c0=0, cols=A, shift=0, r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KK)
-            dyt = Split.zeros((ld, KK), dev)
-            ops.transpose_planes(dqs, z=B, rows=T, src_zstride=T * ld, ld_src=ld, c0=0, cols=ld, shift=0, r_out=T, dst=dyt, dst_zstride=Tp, ld_dst=KK)
-            ops.batched_matmul_nt(xt, dyt, batch=1, heads=1, m=A, n=ld, k=KK,
-                                  a_spec=dict(rows=A, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0),
-                                  b_spec=dict(rows=ld, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0),
-                                  y_f32=gw, y_batch_stride=0, y_head_stride=0, y_ld=ld)
+            Tq, Sq, ksq, KKq = wgrad.plan(B, T, A, ld)
+            xt = Split.zeros((A, KKq), dev)
+            ops.transpose_planes(c["h1"], z=B, rows=T, src_zstride=T * A, ld_src=A, c0=0, cols=A, shift=0, r_out=T, dst=xt, dst_zstride=Tq, ld_dst=KKq)
+            dyt = Split.zeros((ld, KKq), dev)
+            ops.transpose_planes(dqs, z=B, rows=T, src_zstride=T * ld, ld_src=ld, c0=0, cols=ld, shift=0, r_out=T, dst=dyt, dst_zstride=Tq, ld_dst=KKq)
+            gw = wgrad.nt_splitk(xt, dyt, A, ld, Sq, ksq, KKq)
             for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
                 self.grads[q + "self_attn." + nm + ".weight"].copy_(gw[:, j * A:(j + 1) * A])
             ops.layer_norm_bwd(c["x0"], self.P(q + "norm1.weight"), dh1, dx, True, self.grads[q + "norm1.weight"], self.grads[q + "norm1.bias"])

@@ -26,6 +26,7 @@ import torch.distributed as dist
 from .. import _lib, ops
 from ..ops import Split, _ptr, _stream
 from ..modules.audio import STFT
+from . import wgrad
 from .flat import FlatBuffers
 from .fs2_step import pack_dev
 
@@ -102,6 +103,10 @@ class _Net:
 class _ConvOps:
     """Channels-last Conv1D forward / backward through pk_conv_gemm (dilation, 'same' zero padding via TMA bounds)."""
 
+    @staticmethod
+    def _wgrad(dys, x, cout, cin, k, shifts):
+        return _wgrad_splitk(dys, x, cout, cin, k, shifts)
+
     def __init__(self):
         self.packs = {}
 
@@ -144,23 +149,8 @@ class _ConvOps:
             wb = self._pk(("b", name), lambda: pack_dev(_pad8(w.flip(-1).permute(1, 2, 0)).permute(0, 2, 1)))   # [Cin, Cout_p, k]
             dx, _ = ops.conv_gemm(dys, wb, n=cin, k=cout_p, taps=k, dil=dil)
         # weight gradient: dW[:, :, tap] = dY^T . shift(X, (tap - pad) * dil) over the flattened (batch, time) axis
-        cin_p = x.hi.shape[-1]
-        Tp = (T + 63) // 64 * 64
-        KK = B * Tp
-        dyt = Split.zeros((cout_p, KK), dev)
-        ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout_p, ld_src=cout_p, c0=0, cols=cout_p, shift=0, r_out=T, dst=dyt,
-                             dst_zstride=Tp, ld_dst=KK)
         pad = (k - 1) // 2
-        tmp = torch.empty(k, cout_p, cin_p, dtype=torch.float32, device=dev)
-        sy = dict(rows=cout_p, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
-        sx = dict(rows=cin_p, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
-        for tap in range(k):
-            xt = Split.zeros((cin_p, KK), dev)
-            ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin_p, shift=(tap - pad) * dil,
-                                 r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KK)
-            ops.batched_matmul_nt(dyt, xt, batch=1, heads=1, m=cout_p, n=cin_p, k=KK, a_spec=sy, b_spec=sx, y_f32=tmp[tap],
-                                  y_batch_stride=0, y_head_stride=0, y_ld=cin_p)
-        g = tmp[:, :cout, :cin].permute(1, 2, 0)
+        g = self._wgrad(dys, x, cout, cin, k, [(tap - pad) * dil for tap in range(k)])
         if accumulate:
             ops.axpy_(1.0, g.contiguous(), dw)
         else:
@@ -168,9 +158,29 @@ class _ConvOps:
         return dx
 
 
+def _wgrad_splitk(dys, x, cout, cin, k, shifts):
+    """dW (cout, cin, k): dW[:, :, j] = sum_{b, t} dY[b, t, :]^T X[b, t + shifts[j], :], split-K (training/wgrad.py: the reduction
+    runs over batch * time = 10^5 .. 10^6 rows while the output is one or two tiles)."""
+    B, T = dys.hi.shape[0], dys.hi.shape[1]
+    dev = dys.hi.device
+    cout_p, cin_p = dys.hi.shape[-1], x.hi.shape[-1]
+    Tp, S, ks, KKp = wgrad.plan(B, T, cout_p, cin_p)
+    dyt = Split.zeros((cout_p, KKp), dev)
+    ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout_p, ld_src=cout_p, c0=0, cols=cout_p, shift=0, r_out=T, dst=dyt,
+                         dst_zstride=Tp, ld_dst=KKp)
+    out = torch.empty(len(shifts), cout_p, cin_p, dtype=torch.float32, device=dev)
+    for j, sh in enumerate(shifts):
+        xt = Split.zeros((cin_p, KKp), dev)
+        ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin_p, shift=sh, r_out=T, dst=xt,
+                             dst_zstride=Tp, ld_dst=KKp)
+        wgrad.nt_splitk(dyt, xt, cout_p, cin_p, S, ks, KKp, out=out[j])
+    return out[:, :cout, :cin].permute(1, 2, 0)
+
+
 class PWGTrainStep:
     def __init__(self, generator, discriminator, lr_g=1e-4, lr_d=5e-5, eps=1e-6, grad_norm_g=10.0, grad_norm_d=1.0, step_size=200000,
-                 gamma=0.5, lambda_adv=4.0, discriminator_train_start_steps=100000, stft_loss_params=None, process_group=None):
+                 gamma=0.5, lambda_adv=4.0, discriminator_train_start_steps=100000, stft_loss_params=None, process_group=None,
+                 use_graphs=None):
         """Defaults: examples/GANVocoder/parallelwave_gan/baker/conf/default.yaml (optimiser / scheduler / loss sections).
         `discriminator`: a PWGDiscriminator (models/parallel_wavegan.py); both networks must carry weight norm (the reference trains
         the g / v parametrisation)."""
@@ -201,6 +211,12 @@ class PWGTrainStep:
             basis[:, bins_p:bins_p + bins] = -torch.sin(2 * math.pi * k * n / nf)   # d im[k] / d frame[n]
             self.res.append(dict(stft=st, n_fft=nf, hop=hop, bins=bins, bins_p=bins_p, basis=pack_dev(basis.float().to(dev))))
         self.conv = _ConvOps()
+        # forward + backward of each half of update_core replay as a CUDA graph per batch shape (the step is ~2 500 small launches;
+        # the Adam kernels stay outside: their bias correction is a host-computed scalar).  PK_TRAIN_GRAPH=0 disables.
+        import os
+        from ..graph import GraphRunner
+        self._graphs = GraphRunner(max_graphs=8)
+        self.use_graphs = (os.environ.get("PK_TRAIN_GRAPH", "1") != "0") if use_graphs is None else bool(use_graphs)
         if self.world > 1:
             for net in (self.g, self.d):
                 dist.broadcast(net.flat, src=0, group=process_group)
@@ -436,25 +452,7 @@ class PWGTrainStep:
 
     def _wgrad_nopad(self, dy, x, w, dw):
         cout, cin, k = w.shape
-        B, T = dy.shape[0], dy.shape[1]
-        dev = dy.device
-        dys = Split.from_f32(_pad8(dy))
-        cout_p, cin_p = dys.hi.shape[-1], x.hi.shape[-1]
-        Tp = (T + 63) // 64 * 64
-        KK = B * Tp
-        dyt = Split.zeros((cout_p, KK), dev)
-        ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout_p, ld_src=cout_p, c0=0, cols=cout_p, shift=0, r_out=T, dst=dyt,
-                             dst_zstride=Tp, ld_dst=KK)
-        tmp = torch.empty(k, cout_p, cin_p, dtype=torch.float32, device=dev)
-        sy = dict(rows=cout_p, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
-        sx = dict(rows=cin_p, cols=KK, ld=KK, batch_stride=0, batches=1, bmul=0, hmul=0, col0=0, colh=0)
-        for tap in range(k):
-            xt = Split.zeros((cin_p, KK), dev)
-            ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin_p, shift=tap, r_out=T,
-                                 dst=xt, dst_zstride=Tp, ld_dst=KK)
-            ops.batched_matmul_nt(dyt, xt, batch=1, heads=1, m=cout_p, n=cin_p, k=KK, a_spec=sy, b_spec=sx, y_f32=tmp[tap],
-                                  y_batch_stride=0, y_head_stride=0, y_ld=cin_p)
-        dw.copy_(tmp[:, :cout, :cin].permute(1, 2, 0))
+        dw.copy_(_wgrad_splitk(Split.from_f32(_pad8(dy)), x, cout, cin, k, list(range(k))))
 
     # ------------------------------------------------------------------------------------------------------------
     # one update_core
@@ -511,10 +509,22 @@ class PWGTrainStep:
         wav = wav.reshape(wav.shape[0], -1).contiguous()
         if noise is None:
             noise = torch.randn(wav.shape[0], 1, wav.shape[1], device=dev)
-        losses = self.generator_losses_and_grads(noise, mel, wav)
+        adversarial = self.iteration > self.d_start
+        shape = (tuple(noise.shape), tuple(mel.shape))
+
+        def run(tag, fn, names):
+            if not self.use_graphs:
+                return fn(noise, mel, wav)
+            def once(n_, m_, w_):
+                res = fn(n_, m_, w_)
+                return tuple(res[k] for k in names)
+            vals = self._graphs.run((tag, adversarial) + shape, once, [noise, mel, wav])
+            return {k: v.clone() for k, v in zip(names, vals)}
+        g_names = ("spectral_convergence_loss", "log_stft_magnitude_loss") + (("adversarial_loss",) if adversarial else ()) + ("generator_loss",)
+        losses = run("g", self.generator_losses_and_grads, g_names)
         self.g.adam(self._lr(self.lr_g, self.g.steps), self.eps, self.clip_g, self.world, self.group)
-        if self.iteration > self.d_start:
-            losses.update(self.discriminator_losses_and_grads(noise, mel, wav))
+        if adversarial:
+            losses.update(run("d", self.discriminator_losses_and_grads, ("real_loss", "fake_loss", "discriminator_loss")))
             self.d.adam(self._lr(self.lr_d, self.d.steps), self.eps, self.clip_d, self.world, self.group)
         self.iteration += 1
         return losses

@@ -176,7 +176,7 @@ def test_update_core_matches_oracle_update(cuda):
     from oracle import pwg as opwg
     from parakeet_b200.training import PWGTrainStep
     gp, dp, gen, dis, noise, mel, wav = _setup(cuda)
-    ts = PWGTrainStep(gen, dis, discriminator_train_start_steps=0)
+    ts = PWGTrainStep(gen, dis, discriminator_train_start_steps=0, use_graphs=False)
     ts.iteration = 1
     got = ts.update_core((wav, mel), noise=noise.to(cuda))
 
@@ -213,3 +213,27 @@ def test_update_core_matches_oracle_update(cuda):
         assert es[len(es) // 2][1] < 0.05, (name, es[len(es) // 2])
         assert es[0][1] < 0.6 and sum(e > 0.35 for _, e in es) <= 0.03 * len(es), (name, es[:8])
     assert ts.iteration == 2 and ts.g.steps == 1 and ts.d.steps == 1
+
+
+def test_update_core_graph_replay_matches_eager(cuda):
+    """update_core with its two forward + backward halves replayed as CUDA graphs (third call on) against the eager step: the same
+    losses and parameters after four steps, for fresh noise at every step."""
+    from parakeet_b200.training import PWGTrainStep
+    runs = []
+    for graphs in (False, True):
+        gp, dp, gen, dis, noise, mel, wav = _setup(cuda, frames=20)
+        ts = PWGTrainStep(gen, dis, discriminator_train_start_steps=0, use_graphs=graphs)
+        ts.iteration = 1
+        g = torch.Generator().manual_seed(99)
+        losses = []
+        for _ in range(4):
+            nz = torch.randn(noise.shape, generator=g).to(cuda)
+            out = ts.update_core((wav, mel), noise=nz)
+            losses.append([float(out["generator_loss"]), float(out["discriminator_loss"])])
+        runs.append((losses, {k: v.detach().double().cpu().clone() for k, v in gen.state_dict().items()}, ts))
+    assert runs[1][2]._graphs.replays >= 4 and runs[0][2]._graphs.replays == 0
+    assert np.allclose(runs[0][0], runs[1][0], rtol=2e-3), (runs[0][0], runs[1][0])
+    gp0 = _setup(cuda, frames=20)[0]
+    k = "conv_layers.7.conv.weight_v"                                      # compare the parameter DELTAS (Adam sign noise, see above)
+    d_e, d_g = runs[0][1][k] - gp0[k].double(), runs[1][1][k] - gp0[k].double()
+    assert ((d_g - d_e).norm() / d_e.norm()).item() < 0.3
