@@ -90,32 +90,66 @@ def end_tile_start(length):
     return (length - EDGE) // HALF * HALF
 
 
-def compact_band_tables(firs, scales, frames_list):
-    """-> (table (rows, KWIN) float64, layout dict).  Rows [0, P): interior rows by t mod P (P = period(hop));
-    [P, P + 128): the first half tile of any utterance; then END_ROWS rows per entry of `frames_list` (utterance i): the half
-    tiles starting at end_tile_start(L_i), + HALF, + 2 HALF (rows at or past L_i are zero).  `source_row` below is the
-    kernel's lookup."""
+def _reference_rows(firs, scales, width=8, ref_frames=8):
+    """Row windows of an 8-frame utterance: everything any longer utterance's table is assembled from."""
     hop = 1
     for s_ in scales:
         hop *= s_
-    P = period(hop)
-    big = tile_band_table(firs, scales, 2 * (P // hop) + 8)          # long enough for one whole interior period
-    assert big.shape[0] >= 2 * P + EDGE
-    parts = [big[P:2 * P], big[:HALF]]
-    cache = {}
+    return _row_windows(upsample_operator(firs, scales, ref_frames), hop, width), hop, ref_frames
+
+
+def _scatter_rows(rows, t, hop, width=8):
+    """rows (n, width) of samples t (n,) -> (n, KWIN) placed relative to the K window of each sample's pair tile."""
+    shift = (t // hop - 2) - window_start(t // TILE * TILE, hop)
+    assert int(shift.min()) >= 0 and int(shift.max()) + width <= KWIN
+    out = torch.zeros(t.shape[0], KWIN, dtype=torch.float64)
+    out.scatter_(1, shift[:, None] + torch.arange(width)[None, :], rows)
+    return out
+
+
+def end_block(firs, scales, nf, ref=None):
+    """The END_ROWS rows from end_tile_start(L) on of an nf-frame utterance (zero at and past L = nf * hop), built from the
+    8-frame reference rows without materialising the whole per-length table (O(END_ROWS) per distinct length)."""
+    ref, hop, ref_frames = ref if ref is not None else _reference_rows(firs, scales)
+    blk = torch.zeros(END_ROWS, KWIN, dtype=torch.float64)
+    if nf <= 0:
+        return blk
+    L = nf * hop
+    m1 = end_tile_start(L)
+    if nf <= ref_frames or L < 2 * EDGE + hop:
+        full = tile_band_table(firs, scales, nf)
+        n = min(END_ROWS, L - m1)
+        blk[:n] = full[m1:m1 + n]
+        return blk
+    t = torch.arange(m1, L)
+    mid = (ref_frames // 2) * hop
+    rows = torch.where((t >= L - EDGE)[:, None], ref[(ref_frames * hop - (L - t)).clamp(0, ref.shape[0] - 1)], ref[mid + t % hop])
+    blk[:L - m1] = _scatter_rows(rows, t, hop)
+    return blk
+
+
+def compact_band_tables(firs, scales, frames_list, base=None):
+    """-> (table (rows, KWIN) float64, layout dict, base).  Rows [0, P): interior rows by t mod P (P = period(hop));
+    [P, P + 128): the first half tile of any utterance; then END_ROWS rows per entry of `frames_list` (utterance i): the half
+    tiles starting at end_tile_start(L_i), + HALF, + 2 HALF (rows at or past L_i are zero).  `source_row` below is the
+    kernel's lookup.  `base` (returned, reusable): the length-independent part + the reference rows - constants of the model."""
+    if base is None:
+        refpack = _reference_rows(firs, scales)
+        hop = refpack[1]
+        P = period(hop)
+        big = tile_band_table(firs, scales, 2 * (P // hop) + 8)          # long enough for one whole interior period
+        assert big.shape[0] >= 2 * P + EDGE
+        base = dict(head=torch.cat([big[P:2 * P], big[:HALF]]), ref=refpack, hop=hop, period=P, ends={})
+    P = base["period"]
+    parts = [base["head"]]
     for nf in frames_list:
         nf = int(nf)
-        if nf not in cache:
-            L = nf * hop
-            m1 = end_tile_start(L)
-            full = tile_band_table(firs, scales, nf) if nf > 0 else torch.zeros(0, KWIN, dtype=torch.float64)
-            blk = torch.zeros(END_ROWS, KWIN, dtype=torch.float64)
-            if nf > 0:
-                n = min(END_ROWS, L - m1)
-                blk[:n] = full[m1:m1 + n]
-            cache[nf] = blk
-        parts.append(cache[nf])
-    return torch.cat(parts), dict(period=P, start_row=P, end_base=P + HALF, hop=hop)
+        if nf not in base["ends"]:
+            if len(base["ends"]) > 4096:
+                base["ends"].clear()
+            base["ends"][nf] = end_block(firs, scales, nf, base["ref"])
+        parts.append(base["ends"][nf])
+    return torch.cat(parts), dict(period=P, start_row=P, end_base=P + HALF, hop=base["hop"]), base
 
 
 def source_row(m, length, b, layout):

@@ -312,7 +312,7 @@ class PWGGenerator(Layer):
         if ent is None:
             if len(pk["band_tables"]) >= 16:
                 pk["band_tables"].pop(next(iter(pk["band_tables"])))
-            tab, lay = fc.compact_band_tables(pk["firs"], self.upsample_scales, lens_key)
+            tab, lay, pk["band_base"] = fc.compact_band_tables(pk["firs"], self.upsample_scales, lens_key, pk.get("band_base"))
             wide = torch.zeros(tab.shape[0], 64, dtype=torch.float32)
             wide[:, :fc.KWIN] = tab.float()
             ent = pk["band_tables"][lens_key] = (Split.from_f32(wide.to(self.device)), lay)

@@ -298,7 +298,13 @@ def test_pwg_compact_band_tables_equal_the_per_length_tables():
     params = {k: v.double() for k, v in opwg.fold_weight_norm(opwg.synth_params(2, weight_norm=True)).items()}
     firs = [params[f"upsample_net.upsample.up_layers.{2 * i + 1}.weight"].reshape(-1) for i in range(len(scales))]
     frames_list = [1, 2, 3, 7, 9, 40, 64, 65, 129, 400]
-    table, lay = fc.compact_band_tables(firs, scales, frames_list)
+    table, lay, base = fc.compact_band_tables(firs, scales, frames_list)
+    again, _, _ = fc.compact_band_tables(firs, scales, frames_list[::-1], base)            # cached base + end blocks: same rows
+    assert torch.equal(again[:lay["end_base"]], table[:lay["end_base"]]) and torch.equal(again[-384:], table[lay["end_base"]:lay["end_base"] + 384])
+    for nf in (9, 40, 129):                                                                 # the O(384) end block == the full per-length table's tail
+        L, full = nf * 300, fc.tile_band_table(firs, scales, nf)
+        m1 = fc.end_tile_start(L)
+        assert torch.equal(fc.end_block(firs, scales, nf)[:L - m1], full[m1:])
     assert lay["period"] == 19200 and table.shape[0] == 19200 + 128 + 384 * len(frames_list)
     for b, nf in enumerate(frames_list):
         L = nf * lay["hop"]
