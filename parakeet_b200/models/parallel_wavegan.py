@@ -189,6 +189,7 @@ class PWGGenerator(Layer):
         ws = self._ws.get(key)
         if ws is None:
             self._ws.clear()
+            self._graphs.clear()          # captured forwards point into the old workspace
             dev = self.device
             ws = dict(xa=Split.zeros((B, T, 64), dev), xb=Split.zeros((B, T, 64), dev),
                       c=Split.empty((B, T, self.aux_channels), dev) if not self._frame_cond() else None,   # sample-rate planes: legacy path only
@@ -208,18 +209,39 @@ class PWGGenerator(Layer):
         """x: (B, 1, T) noise, c: (B, aux, T' + 2*aux_context_window) -> (B, 1, T).
 
         `lens` (optional, int32 (B,) valid samples per utterance) lets a ragged batch run as one call: every
-        utterance is then generated exactly as if it were alone (zero padding at its own end)."""
+        utterance is then generated exactly as if it were alone (zero padding at its own end).
+
+        A repeated (B, T, lengths) replays as ONE CUDA graph (eager the first time, captured the second): the forward is ~40
+        launches, each with a handful of tensor-map encodes on the host - invisible at batch 32 x 400 frames (33 ms of GPU work),
+        but most of the latency of a single utterance or of a 4-utterance shard."""
         _declare()
-        L = _lib.lib()
         if not (x.is_cuda and c.is_cuda):
             raise _lib.PkError("PWGGenerator.forward needs CUDA tensors (no CPU fallback)")
-        pk = self._pack()
         B, _, T = x.shape
         frames = c.shape[-1] - 2 * self.aux_context_window
         assert frames * self.upsample_factor == T, (c.shape, x.shape)   # reference :462
+        lens_key = None
+        if lens is not None:
+            assert lens.dtype == torch.int32 and lens.is_cuda
+            # host copy of the lengths: they select the band-table end blocks (lengths are host data in the reference's callers
+            # too, synthesize.py:96-104)
+            lens_key = tuple(int(v) for v in torch.div(lens, self.upsample_factor, rounding_mode="floor").cpu().tolist())
+        eager = (not self._frame_cond() or getattr(self, "_layer_events", None) is not None or getattr(self, "_prof", None) is not None)
+        if eager:
+            return self._forward_impl(x, c, lens, lens_key)
+        fn = lambda x_, c_, *l_: self._forward_impl(x_, c_, l_[0] if l_ else None, lens_key)   # noqa: E731
+        out = self._graphs.run(("fwd", B, T, lens_key), fn, [x.contiguous().float(), c.contiguous().float()] + ([lens] if lens is not None else []))
+        return out.clone()
+
+    def _forward_impl(self, x, c, lens, lens_key):
+        L = _lib.lib()
+        pk = self._pack()
+        B, _, T = x.shape
+        frames = c.shape[-1] - 2 * self.aux_context_window
         fcond = self._frame_cond()
         if self._ws and (next(iter(self._ws.values()))["c"] is None) != fcond:
             self._ws.clear()                                         # the toggle changed between calls
+            self._graphs.clear()
         ws = self._workspace(B, T)
         st = _stream()
         x = x.contiguous().float()
@@ -227,7 +249,6 @@ class PWGGenerator(Layer):
         lens_p = _ptr(lens) if lens is not None else None
         frame_lens = None
         if lens is not None:
-            assert lens.dtype == torch.int32 and lens.is_cuda
             frame_lens = torch.div(lens, self.upsample_factor, rounding_mode="floor").to(torch.int32)
         _lib.check(L.pk_pwg_upsample(_ptr(c), _ptr(pk["conv_in_w"]), pk["fir_host"].ctypes.data_as(C.c_void_p),
                                      pk["scales_host"].ctypes.data_as(C.c_void_p), len(self.upsample_scales), B,
@@ -241,7 +262,7 @@ class PWGGenerator(Layer):
             ws["xb"].lo.zero_()
         src, dst = ws["xa"], ws["xb"]
         if fcond:
-            return self._forward_frame_cond(pk, ws, src, dst, B, T, frames, lens, frame_lens, st)
+            return self._forward_frame_cond(pk, ws, src, dst, B, T, frames, lens, frame_lens, st, lens_key)
         args = PwgLayerArgs()
         args.batch, args.t, args.aux_channels = B, T, self.aux_channels
         args.lens = lens.data_ptr() if lens is not None else None
@@ -270,7 +291,7 @@ class PWGGenerator(Layer):
         self._last_x = src  # layer-30 residual stream (tests)
         return out
 
-    def _forward_frame_cond(self, pk, ws, src, dst, B, T, frames, lens, frame_lens, st):
+    def _forward_frame_cond(self, pk, ws, src, dst, B, T, frames, lens, frame_lens, st, lens_key=None):
         """Residual stack with frame-rate conditioning (csrc/pwg_fc.cu): conv1x1_aux of all 30 layers is applied
         to conv_in(mel) at frame rate by ONE GEMM per forward (P), and each layer multiplies the band table of the (linear,
         per-channel) upsampling operator with the 16-frame window of P its tile touches - no sample-rate conditioning tensor."""
@@ -303,15 +324,13 @@ class PWGGenerator(Layer):
         ops.batched_matmul_nt(pk["aux_all"], m1s, batch=B, heads=1, m=NL * 128, n=frames, k=A, a_spec=a_spec, b_spec=b_spec,
                               y_split=P, y_batch_stride=NL * 128 * Fp, y_head_stride=0, y_ld=Fp)
         # compact band table (constants of the model + the utterance lengths of this batch; a few MB, cached per length tuple)
-        if frame_lens is None:
+        if lens_key is None:
             lens_key = (frames,) * B
-        else:
-            lens_key = tuple(int(v) for v in frame_lens.cpu().tolist())   # host sync: ragged batches only (lengths are host data
-                                                                           # in the reference's callers too, synthesize.py:96-104)
         ent = pk["band_tables"].get(lens_key)
         if ent is None:
             if len(pk["band_tables"]) >= 16:
                 pk["band_tables"].pop(next(iter(pk["band_tables"])))
+                self._graphs.clear()      # a captured forward may point at the evicted table
             tab, lay, pk["band_base"] = fc.compact_band_tables(pk["firs"], self.upsample_scales, lens_key, pk.get("band_base"))
             wide = torch.zeros(tab.shape[0], 64, dtype=torch.float32)
             wide[:, :fc.KWIN] = tab.float()
