@@ -288,6 +288,8 @@ class PWGGenerator(Layer):
         out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
         _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
+        if lens is not None:
+            ops.mask_rows_(out.reshape(B, T, 1), lens)
         self._last_x = src  # layer-30 residual stream (tests)
         return out
 
@@ -363,6 +365,8 @@ class PWGGenerator(Layer):
         out = torch.empty(B, 1, T, dtype=torch.float32, device=self.device)
         _lib.check(L.pk_pwg_tail(_ptr(ws["skip"]), _ptr(pk["skip_bias_sum"]), _ptr(pk["tail_w1"]), _ptr(pk["tail_b1"]), _ptr(pk["tail_w2"]),
                                  _ptr(pk["tail_b2"]), math.sqrt(1.0 / self.layers), B * T, _ptr(out), st), "pk_pwg_tail")
+        if lens is not None:
+            ops.mask_rows_(out.reshape(B, T, 1), lens)       # samples past an utterance's end: zero, not tail(bias)
         self._last_x = src
         return out
 

@@ -75,6 +75,41 @@ def test_pwg_ragged_batch_equals_single_utterances(cuda, pwg):
         assert rel_err(y[i, :, :f * hop], refs[i]) < TOL
 
 
+def test_pwg_ragged_batch_graph_replay_and_empty_utterance(cuda, pwg):
+    """A ragged batch holding an EMPTY utterance, run three times (eager, CUDA-graph capture, replay): every call reproduces the
+    single-utterance oracle results, the empty row stays zero, and a different set of lengths of the same padded shape (another
+    graph key, other band-table end blocks) is not confused with the first."""
+    from oracle import pwg as opwg
+    gen, folded = pwg
+    hop = 300
+
+    def make(frames, seed):
+        xs = torch.zeros(len(frames), 1, 40 * hop)
+        cs = torch.zeros(len(frames), 80, 44)
+        refs = []
+        for i, f in enumerate(frames):
+            if f == 0:
+                refs.append(None)
+                continue
+            xi, ci = opwg.synth_inputs(seed + i, batch=1, mel_frames=f)
+            xs[i, :, :f * hop], cs[i, :, :f + 4] = xi[0], ci[0]
+            with torch.no_grad():
+                refs.append(opwg.generator_forward(folded, xi, ci)[0])
+        return xs.to(cuda), cs.to(cuda), torch.tensor([f * hop for f in frames], dtype=torch.int32, device=cuda), refs
+    for frames, seed in (([40, 0, 33], 30), ([21, 40, 1], 40)):
+        xs, cs, lens, refs = make(frames, seed)
+        replays0 = gen._graphs.replays
+        for call in range(3):
+            y = gen(xs, cs, lens=lens)
+            for i, f in enumerate(frames):
+                if f == 0:
+                    assert y[i].abs().max().item() == 0
+                else:
+                    assert rel_err(y[i, :, :f * hop], refs[i]) < TOL, (frames, call, i)
+                    assert y[i, :, f * hop:].abs().max().item() == 0 if f < 40 else True
+        assert gen._graphs.replays > replays0
+
+
 def test_pwg_full_size_properties(cuda, pwg):
     """cfg2 (B=32, 400 frames -> 3.84 M samples): batch independence + determinism + one utterance vs the oracle."""
     from oracle import pwg as opwg
