@@ -338,6 +338,39 @@ int pk_waveflow_layer_update(const float* o, int64_t rows, int32_t c, float* sta
 int pk_waveflow_row_out(const float* skip, const float* w, const float* bias, const float* z_row, int64_t z_batch_stride,
                         int32_t batch, int32_t width, int32_t c, float* x_next, int64_t x_batch_stride, pk_stream_t stream);
 
+/* One whole ResidualBlock.add_input (:248-285) as ONE CTA-pair kernel (channels == 64; the default layer path of
+ * ConditionalWaveFlow.inverse, PK_WF_FUSED=0 selects the pk_conv_gemm_ex pair above):
+ *   a | g = conv2d(3-row ring, dilation (1, 2^l)) + condition_proj(condition row) + bias1;  z = tanh(a) sigmoid(g);
+ *   skip | res = out_proj(z) + bias2;  skip accumulator (=|+=) skip;  ring slot `slot` of the NEXT layer <- row + res.
+ * buf planes (batch, width, 192) hold this layer's ring (slot s in columns [64 s, 64 s + 64)); `slot` is the newest row's slot
+ * (the residual input).  cond planes: the condition row (batch, width, n_mels), batch stride cond_batch_stride elements.
+ * Every pair of planes comes from ONE allocation (lo after hi).
+ * w1 planes (128, 704): row n = gate channel (a: 0..63, g: 64..127); columns [192 tap + 64 s + c] = conv.weight[n, c, kh(s), tap]
+ * for the ring slot s holding kernel row kh(s) at this row step, columns [576 + m] = condition_proj.weight[n, m] (zeros from
+ * n_mels to 128).  w2 planes (128, 64): out_proj.weight with rows reordered to skip (0..63) | res (64..127).
+ * bias1 / bias2: HOST pointers [128] (conv.bias + condition_proj.bias; out_proj.bias as skip | res), copied into the kernel
+ * parameter block.  next_hi / next_lo: the next layer's ring planes, or NULL (last layer).  skip fp32 (batch, width, 64). */
+typedef struct pk_waveflow_layer_args {
+  int32_t batch, width, channels, n_mels, dilation, slot;
+  const void* buf_hi;
+  const void* buf_lo;
+  const void* cond_hi;
+  const void* cond_lo;
+  int64_t cond_batch_stride;
+  const void* w1_hi;
+  const void* w1_lo;
+  const void* w2_hi;
+  const void* w2_lo;
+  const float* bias1;
+  const float* bias2;
+  void* next_hi;
+  void* next_lo;
+  float* skip;
+  int32_t skip_init;
+  void* prof;              /* debug: NULL, or device uint64[8]: MMA-issuer cycles [0] issue, [1] wait data, [2] wait acc2, [3] wait z; [4] tiles */
+} pk_waveflow_layer_args;
+int pk_waveflow_layer(const pk_waveflow_layer_args* args, pk_stream_t stream);
+
 /* FastSpeech2Loss.forward with use_masking=True (models/fastspeech2/fastspeech2.py:701-812; DurationPredictorLoss
  * duration_predictor.py:140-184): out4 = { l1_loss = L1(before, ys) + L1(after, ys) over valid frames,
  * duration_loss = MSE(d_outs, log(ds + 1)), pitch_loss = MSE(p_outs, ps), energy_loss = MSE(e_outs, es) over valid tokens }.

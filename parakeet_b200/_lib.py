@@ -75,6 +75,15 @@ class PwgLayerFcArgs(C.Structure):
                 ("bias1", C.c_void_p), ("bias2", C.c_void_p), ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
 
 
+class WaveflowLayerArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32), ("n_mels", C.c_int32),
+                ("dilation", C.c_int32), ("slot", C.c_int32), ("buf_hi", C.c_void_p), ("buf_lo", C.c_void_p),
+                ("cond_hi", C.c_void_p), ("cond_lo", C.c_void_p), ("cond_batch_stride", C.c_int64),
+                ("w1_hi", C.c_void_p), ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p),
+                ("bias1", C.c_void_p), ("bias2", C.c_void_p), ("next_hi", C.c_void_p), ("next_lo", C.c_void_p),
+                ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
+
+
 def _declare(L):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
@@ -88,6 +97,7 @@ def _declare(L):
         "pk_pwg_first_conv": [vp, vp, vp, vp, i32, i32, vp, vp, vp],
         "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
         "pk_pwg_residual_layer_fc": [C.POINTER(PwgLayerFcArgs), vp],
+        "pk_waveflow_layer": [C.POINTER(WaveflowLayerArgs), vp],
         "pk_pwg_tail": [vp, vp, vp, vp, vp, vp, f32, i64, vp, vp],
         "pk_embed_pe": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],

@@ -8,12 +8,23 @@ state-dict keys (`encoder.{i}.{weight_g,weight_v,bias}`, `decoder.{f}.input_proj
 Supported this round: kernel_size (3, 3) and n_group in {8, 16} (height dilation 1 -> a 3-row causal buffer), which
 covers the shipped config (examples/waveflow/config.py).  Training (`forward`, WaveFlowLoss) is not implemented.
 """
+import ctypes as C_
+import os
+
 import numpy as np
 import torch
 
 from .. import _lib, ops
 from ..layer import Layer
 from ..ops import Split, _ptr, _stream
+
+
+def _planes(m, dev):
+    """fp32 matrix -> split-bf16 planes (2, rows, cols) in ONE allocation (the 4-D TMA maps of the fused kernels need it)."""
+    m = m.detach().float().cpu()
+    hi = m.to(torch.bfloat16)
+    lo = (m - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous().to(dev)
 
 
 def _fold_wn(params):
@@ -99,7 +110,24 @@ class ConditionalWaveFlow(Layer):
                     for s in range(3):
                         wk[:, s * C:(s + 1) * C, :] = w[:, :, (s - v) % 3, :]
                     variants.append(ops.pack_weight(wk, dev))
-                layers.append(dict(conv=variants, conv_b=p[q + "conv.bias"].to(dev),
+                fused = None
+                if self._fusable():
+                    # operands of pk_waveflow_layer (include/parakeet_b200.h): GEMM1 weight per row-step variant =
+                    # [tap][slot][c] conv columns | condition_proj columns, both planes in one allocation; out_proj as skip | res
+                    cw = p[q + "condition_proj.weight"][:, :, 0, 0]
+                    w1 = []
+                    for v in range(3):
+                        m = torch.zeros(2 * C, 11 * 64)
+                        for tap in range(3):
+                            for s in range(3):
+                                m[:, 192 * tap + 64 * s:192 * tap + 64 * s + 64] = w[:, :, (s - v) % 3, tap]
+                        m[:, 576:576 + self.n_mels] = cw
+                        w1.append(_planes(m, dev))
+                    ow, ob = p[q + "out_proj.weight"][:, :, 0, 0], p[q + "out_proj.bias"]
+                    fused = dict(w1=w1, w2=_planes(torch.cat([ow[C:], ow[:C]], dim=0), dev),
+                                 b1=(p[q + "conv.bias"] + p[q + "condition_proj.bias"]).numpy().astype("float32").copy(),
+                                 b2=torch.cat([ob[C:], ob[:C]]).numpy().astype("float32").copy())
+                layers.append(dict(fused=fused, conv=variants, conv_b=p[q + "conv.bias"].to(dev),
                                    cond=ops.pack_weight(p[q + "condition_proj.weight"][:, :, 0, 0], dev),
                                    cond_b=p[q + "condition_proj.bias"].to(dev),
                                    out=ops.pack_weight(p[q + "out_proj.weight"][:, :, 0, 0], dev), out_b=p[q + "out_proj.bias"].to(dev)))
@@ -114,6 +142,12 @@ class ConditionalWaveFlow(Layer):
         pk["perms"] = [torch.tensor(pm, dtype=torch.int64, device=dev) for pm in self.perms]   # device-side gather indices
         self._packed = pk
         return pk
+
+    def _fusable(self):
+        """pk_waveflow_layer (one kernel per ResidualBlock.add_input) covers 64 residual channels and 64 < n_mels <= 128;
+        PK_WF_FUSED=0 keeps the two-GEMM path for A/B runs."""
+        return (self.channels == 64 and 64 < self.n_mels <= 128 and self.n_mels % 8 == 0
+                and os.environ.get("PK_WF_FUSED", "1") != "0")
 
     def encode(self, mel, trim_conv_artifact=True):
         """UpsampleNet.forward (:103-132): (B, n_mels, T') -> (B, n_mels, T)."""
@@ -148,6 +182,8 @@ class ConditionalWaveFlow(Layer):
         zt = Split.empty((B, W, C), dev)
         bufs = [Split.zeros((B, W, 3 * C), dev) for _ in range(NL)]
         st = _stream()
+        fused = self._fusable()
+        prof = getattr(self, "_prof", None)                                               # debug: device uint64[8] phase counters
         for fi in reversed(range(self.n_flows)):
             perm = self.perms[fi]
             z = z.index_select(1, pk["perms"][fi])                                        # geo.shuffle_dim(z, 2, perm)
@@ -164,6 +200,25 @@ class ConditionalWaveFlow(Layer):
                                                     _ptr(state), _ptr(bufs[0].hi), _ptr(bufs[0].lo), 3 * C, slot * C, st),
                            "pk_waveflow_input_proj")
                 c_row = Split(cond_s.hi[:, cmap[i]], cond_s.lo[:, cmap[i]])              # (B, W, n_mels) views, batch stride G*W*n_mels
+                if fused:
+                    for l, lay in enumerate(fw["layers"]):
+                        f = lay["fused"]
+                        a = _lib.WaveflowLayerArgs()
+                        a.batch, a.width, a.channels, a.n_mels, a.dilation, a.slot = B, W, C, self.n_mels, 2 ** l, slot
+                        a.buf_hi, a.buf_lo = _ptr(bufs[l].hi), _ptr(bufs[l].lo)
+                        a.cond_hi, a.cond_lo, a.cond_batch_stride = _ptr(c_row.hi), _ptr(c_row.lo), G * W * self.n_mels
+                        w1 = f["w1"][i % 3]
+                        a.w1_hi, a.w1_lo, a.w2_hi, a.w2_lo = _ptr(w1[0]), _ptr(w1[1]), _ptr(f["w2"][0]), _ptr(f["w2"][1])
+                        a.bias1, a.bias2 = f["b1"].ctypes.data, f["b2"].ctypes.data
+                        if l + 1 < NL:
+                            a.next_hi, a.next_lo = _ptr(bufs[l + 1].hi), _ptr(bufs[l + 1].lo)
+                        a.skip, a.skip_init = _ptr(skip), 1 if l == 0 else 0
+                        if prof is not None:
+                            a.prof = _ptr(prof)
+                        _lib.check(L.pk_waveflow_layer(C_.byref(a), st), "pk_waveflow_layer")
+                    _lib.check(L.pk_waveflow_row_out(_ptr(skip), _ptr(fw["out_w"]), _ptr(fw["out_b"]), _ptr(z[:, i]), G * W, B, W, C,
+                                                     _ptr(x[:, i]), G * W, st), "pk_waveflow_row_out")
+                    continue
                 ops.conv_gemm(c_row, fw["cond_all"], n=NL * 2 * C, k=self.n_mels, bias=fw["cond_all_b"], y_f32=h_all)
                 for l, lay in enumerate(fw["layers"]):
                     # dilated conv over the 3-row ring + condition slice -> tanh * sigmoid, fused in the GEMM epilogue
