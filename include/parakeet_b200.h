@@ -371,6 +371,42 @@ typedef struct pk_waveflow_layer_args {
 } pk_waveflow_layer_args;
 int pk_waveflow_layer(const pk_waveflow_layer_args* args, pk_stream_t stream);
 
+/* All row steps i = 1 .. n_group-1 of one Flow.inverse (:515-556) in ONE persistent dataflow launch (the default path of
+ * ConditionalWaveFlow.inverse for 64 channels; PK_WF_FUSED=layer selects one pk_waveflow_layer launch per layer and row).
+ * Per row step: the n_layers ResidualBlock.add_input of pk_waveflow_layer, then on the completed skip sum
+ * (logs, b) = output_proj(skip), x[:, i] = (z[:, i] - b) exp(-logs) (:496-510) and input_proj(x[:, i]) (:437-442) into the
+ * first layer's ring slot i mod 3.  The caller provides row 0: x[:, 0] = z[:, 0], input_proj(x[:, 0]) in slot 0 of ring 0
+ * (pk_waveflow_input_proj), all other ring contents zero, and `flags` (one uint32 per tile: (n_group - 1) * n_layers *
+ * batch * ceil(width / 256)) zeroed.  z / x: fp32 (batch, n_group, width).  cond planes (batch, n_group, width, n_mels);
+ * cond_rows[i] (HOST) = the condition row used at row step i.  ring / w1 / w2 / bias1 / bias2: HOST arrays indexed by layer
+ * (w1: 3 * layer + variant, variant = i mod 3) of the per-layer pointers of pk_waveflow_layer_args (biases: HOST floats).
+ * in_w / in_b [64], out_w [2][64], out_b [2]: HOST floats. */
+typedef struct pk_waveflow_flow_args {
+  int32_t batch, width, channels, n_mels, n_layers, n_group;
+  const int32_t* cond_rows;
+  void* const* ring_hi;
+  void* const* ring_lo;
+  const void* cond_hi;
+  const void* cond_lo;
+  const void* const* w1_hi;
+  const void* const* w1_lo;
+  const void* const* w2_hi;
+  const void* const* w2_lo;
+  const float* const* bias1;
+  const float* const* bias2;
+  const float* in_w;
+  const float* in_b;
+  const float* out_w;
+  const float* out_b;
+  const float* z;
+  float* x;
+  float* skip;
+  uint32_t* flags;
+  int64_t flags_len;
+  void* prof;              /* debug: as in pk_waveflow_layer_args */
+} pk_waveflow_flow_args;
+int pk_waveflow_flow(const pk_waveflow_flow_args* args, pk_stream_t stream);
+
 /* FastSpeech2Loss.forward with use_masking=True (models/fastspeech2/fastspeech2.py:701-812; DurationPredictorLoss
  * duration_predictor.py:140-184): out4 = { l1_loss = L1(before, ys) + L1(after, ys) over valid frames,
  * duration_loss = MSE(d_outs, log(ds + 1)), pitch_loss = MSE(p_outs, ps), energy_loss = MSE(e_outs, es) over valid tokens }.

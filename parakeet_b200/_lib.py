@@ -84,6 +84,16 @@ class WaveflowLayerArgs(C.Structure):
                 ("skip", C.c_void_p), ("skip_init", C.c_int32), ("prof", C.c_void_p)]
 
 
+class WaveflowFlowArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32), ("n_mels", C.c_int32),
+                ("n_layers", C.c_int32), ("n_group", C.c_int32), ("cond_rows", C.c_void_p), ("ring_hi", C.c_void_p),
+                ("ring_lo", C.c_void_p), ("cond_hi", C.c_void_p), ("cond_lo", C.c_void_p), ("w1_hi", C.c_void_p),
+                ("w1_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p), ("bias1", C.c_void_p),
+                ("bias2", C.c_void_p), ("in_w", C.c_void_p), ("in_b", C.c_void_p), ("out_w", C.c_void_p),
+                ("out_b", C.c_void_p), ("z", C.c_void_p), ("x", C.c_void_p), ("skip", C.c_void_p), ("flags", C.c_void_p),
+                ("flags_len", C.c_int64), ("prof", C.c_void_p)]
+
+
 def _declare(L):
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
@@ -98,6 +108,7 @@ def _declare(L):
         "pk_pwg_residual_layer": [C.POINTER(PwgLayerArgs), vp],
         "pk_pwg_residual_layer_fc": [C.POINTER(PwgLayerFcArgs), vp],
         "pk_waveflow_layer": [C.POINTER(WaveflowLayerArgs), vp],
+        "pk_waveflow_flow": [C.POINTER(WaveflowFlowArgs), vp],
         "pk_pwg_tail": [vp, vp, vp, vp, vp, vp, f32, i64, vp, vp],
         "pk_embed_pe": [vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
         "pk_layer_norm": [vp, vp, vp, f32, vp, i32, i32, i32, vp, vp, vp, vp],

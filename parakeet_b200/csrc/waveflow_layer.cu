@@ -17,6 +17,7 @@
 //     running row lives in the ring slot as hi + lo, 16 mantissa bits, re-split after every layer);
 //   * GEMM2's B operand is out_proj with its rows reordered to [skip | res] so that the accumulator halves line up with the
 //     two groups of store warps.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -385,6 +386,456 @@ waveflow_layer_kernel(const __grid_constant__ CUtensorMap tm_x,    // ring plane
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// pk_waveflow_flow: ALL row steps x layers of one Flow.inverse (:515-556) in ONE persistent launch.
+//
+// Layer-step s = (row step, layer) touches, for a 256-position tile, only the tiles m-1, m, m+1 of step s-1 (width dilation
+// <= 128, the row boundary - output_proj, inverse transform, input_proj - is pointwise), so the (G-1) x L steps run as a
+// DATAFLOW over tiles instead of (G-1) x (L+2) grid-wide launches: tile T = s * tiles_per_step + (b, m) is processed by pair
+// T mod n_pairs; its TMA producers first acquire the completion counters of the (up to) three tiles they read from; the store
+// warps publish a tile with a gpu-scope release once its rows are written.  All pairs are co-resident (the grid is sized by
+// cudaOccupancyMaxActiveClusters) and every pair walks its tiles in increasing T, so the lowest unfinished tile can always
+// run.  Gone with the launches: their prologues, the drain of each launch's last wave (400 pair tiles over 74 pairs = 5.4
+// waves, 10 % idle) and the separate row_out / input_proj passes - the last layer's skip warps finish the row in registers.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxLayers = 8;
+constexpr int kMaxGroup = 16;
+constexpr unsigned kTileDone = 2 * kStoreWarps;              // arrivals on a tile's counter: the store warps of both CTAs
+
+struct FlowArgs {
+  CUtensorMap tm_x[kMaxLayers];          // ring planes of each layer (batch, w, 192)
+  CUtensorMap tm_w1[kMaxLayers][3];      // GEMM1 weight planes per layer and row-step variant
+  CUtensorMap tm_w2[kMaxLayers];         // out_proj planes (128, 64): skip | res
+  CUtensorMap tm_c;                      // condition planes as (batch * n_group, w, n_mels): one row of one utterance per index
+  int batch, w, n_layers, n_rows, n_group, tiles_per_b, tiles_per_step, total_tiles, cond_ksteps_last;
+  int serial;                            // 1: GEMM2(i) is issued before GEMM1(i+1) (tiny problems, see the host code)
+  int cmap[kMaxGroup];                   // condition row (after the flows' permutations) of row step i
+  float gate_c[kMaxLayers][128];
+  float out_b[kMaxLayers][128];
+  float in_w[kC], in_b[kC];              // input_proj (1 -> 64)
+  float po_w[2 * kC], po_b[2];           // output_proj (64 -> logs, b)
+  float k_a, k_g;
+  float* skip;
+  const float* z;                        // (batch, n_group, w) rows of this flow's input
+  float* x;                              // (batch, n_group, w) rows of its output; row 0 is filled by the caller
+  __nv_bfloat16* ring_hi[kMaxLayers];
+  __nv_bfloat16* ring_lo[kMaxLayers];
+  unsigned* flags;                       // [total_tiles] completion counters, zeroed by the caller
+  unsigned long long* prof;
+};
+
+struct FlowTile {
+  int s, l, r, b, m0, mt;
+  __device__ void decode(const FlowArgs& p, int t) {
+    s = t / p.tiles_per_step;
+    const int rem = t - s * p.tiles_per_step;
+    r = s / p.n_layers;
+    l = s - r * p.n_layers;
+    b = rem / p.tiles_per_b;
+    mt = rem - b * p.tiles_per_b;
+    m0 = mt * 256;
+  }
+};
+
+// GEMM1 chunk order: the centre tap comes last among the taps - its newest-slot chunk also feeds the residual pass, which
+// needs GEMM2's accumulator of tile i-2 back from the store warps (the later, the more slack)
+__device__ __forceinline__ int chunk_tap(int j) { return j < 3 ? 0 : j < 6 ? 2 : 1; }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_inc(unsigned* ptr) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ptr) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* ptr) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_tile_done(const unsigned* flag) {
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(flag) < kTileDone) {
+    __nanosleep(64);
+    if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a dependency that never completes is a scheduling bug - fail loudly, do not hang
+      printf("pk_waveflow_flow: tile dependency timed out (block %d)\n", static_cast<int>(blockIdx.x));
+      __trap();
+    }
+  }
+}
+
+template <bool kProf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+waveflow_flow_kernel(const __grid_constant__ FlowArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w2 = smem + kStages * kStageBytes;            // [hi | lo] this CTA's 64 rows of the current out_proj
+  const uint32_t ident = w2 + 2 * kWTile;
+  const uint32_t bars = ident + kWTile;
+  const uint32_t full_bar = bars;                              // [stages]   (leader's copy is the live one)
+  const uint32_t empty_bar = full_bar + 8 * kStages;           // [stages]
+  const uint32_t acc1_full = empty_bar + 8 * kStages;          // [2]
+  const uint32_t acc2_full = acc1_full + 16;                   // [2]
+  const uint32_t acc2_empty = acc2_full + 16;                  // [2] leader
+  const uint32_t z_full = acc2_empty + 16;                     // [2] leader
+  const uint32_t w2_full = z_full + 16;                        // leader: both halves of out_proj of the next step landed
+  const uint32_t w2_empty = w2_full + 8;                       // both: the GEMM2s reading the previous out_proj are complete
+  const uint32_t tmem_slot = w2_empty + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = static_cast<int>(blockIdx.x >> 1), n_pairs = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init_a(acc1_full + 8 * i, 1);
+      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, 2 * kStoreWarps);
+      mbar_init_a(z_full + 8 * i, 2 * kGateWarps);
+    }
+    mbar_init_a(w2_full, 1); mbar_init_a(w2_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm_a<512>(tmem_slot);
+  if (threadIdx.x >= 128 && threadIdx.x < 192) {
+    const int n = threadIdx.x - 128;     // [0 | I], as in waveflow_layer_kernel
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (rank == 1 && (n >> 3) == c) {
+        const uint32_t one = (n & 1) ? 0x3f800000u : 0x00003f80u;
+        const int wd = (n & 7) >> 1;
+        v.x = wd == 0 ? one : 0; v.y = wd == 1 ? one : 0; v.z = wd == 2 ? one : 0; v.w = wd == 3 ? one : 0;
+      }
+      sts_u4(ident + n * kSwizzleBytes + ((c ^ (n & 7)) * 16), v);
+    }
+    fence_proxy_async_all();
+  }
+  tcgen05_fence_before();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = lds_u32(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer (both CTAs: own positions, own weight rows) ------------------------------
+      uint32_t it = 0;
+      const uint32_t full_leader = mapa_shared(full_bar, 0);
+      const uint32_t w2_full_leader = mapa_shared(w2_full, 0);
+      int n_w2 = 0;            // out_proj loads issued so far
+      int pend = -1;           // layer whose out_proj is loaded once the GEMM2s of the previous step are known to be complete
+      int prev_s = -1;
+      auto load_w2 = [&](int l) {
+        if (n_w2 > 0) mbar_wait_a(w2_empty, (n_w2 - 1) & 1);
+        if (leader) mbar_arrive_expect_tx_a(w2_full, 2 * 2 * kWTile);
+        tma_load_4d_2sm_a(w2, &p.tm_w2[l], w2_full_leader, 0, 64 * static_cast<int>(rank), 0, 0);
+        ++n_w2;
+      };
+      FlowTile t;
+      for (int T = pair; T < p.total_tiles; T += n_pairs) {
+        t.decode(p, T);
+        if (t.s > 0) {
+          // the rows this tile reads were written by tiles mt-1 .. mt+1 of the previous step (other pairs, generic-proxy stores)
+          const unsigned* f = p.flags + (T - p.tiles_per_step);
+          const bool lo = t.mt > 0, hi = t.mt + 1 < p.tiles_per_b;
+          const bool ready = (!lo || ld_acquire_gpu(f - 1) >= kTileDone) && ld_acquire_gpu(f) >= kTileDone &&
+                             (!hi || ld_acquire_gpu(f + 1) >= kTileDone);
+          if (!ready) {
+            // a tile this one waits for may be the pair's own previous tile, which cannot finish without its out_proj
+            if (pend >= 0) {
+              load_w2(pend);
+              pend = -1;
+            }
+            if (lo) wait_tile_done(f - 1);
+            wait_tile_done(f);
+            if (hi) wait_tile_done(f + 1);
+          }
+          fence_proxy_async_all();       // ... and are read here through the async proxy
+        }
+        const int row0 = t.m0 + 128 * static_cast<int>(rank);
+        const int variant = (t.r + 1) % 3;                     // row step i = r + 1
+        const int crow = t.b * p.n_group + p.cmap[t.r + 1];
+        if (prev_s < 0) load_w2(t.l);
+        for (int j = 0; j < kChunks; ++j, ++it) {
+          const int s = it % kStages;
+          mbar_wait_a(empty_bar + 8 * s, ((it / kStages) & 1) ^ 1);
+          if (j == 4 && pend >= 0) {     // GEMM1 of this tile has started, so GEMM2 of the tile before the previous one is complete
+            load_w2(pend);
+            pend = -1;
+          }
+          const uint32_t st = smem + s * kStageBytes;
+          const uint32_t fb = full_leader + 8 * s;
+          if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kStageBytes);
+          if (j < 9) {
+            const int tap = chunk_tap(j), sl = j % 3;
+            tma_load_4d_2sm_a(st, &p.tm_x[t.l], fb, sl * kC, row0 + (tap - 1) * (1 << t.l), t.b, 0);
+            tma_load_4d_2sm_a(st + 2 * kATile, &p.tm_w1[t.l][variant], fb, (3 * tap + sl) * kChunkK, 64 * static_cast<int>(rank), 0, 0);
+          } else {
+            tma_load_4d_2sm_a(st, &p.tm_c, fb, (j - 9) * kChunkK, row0, crow, 0);
+            tma_load_4d_2sm_a(st + 2 * kATile, &p.tm_w1[t.l][variant], fb, j * kChunkK, 64 * static_cast<int>(rank), 0, 0);
+          }
+        }
+        if (prev_s >= 0 && t.s != prev_s) pend = t.l;
+        prev_s = t.s;
+      }
+      if (pend >= 0) load_w2(pend);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+      constexpr uint32_t idesc = make_idesc_bf16_f32(256, 128);
+      uint32_t it = 0;
+      long long tacc[4] = {0, 0, 0, 0};
+      long long tlast = clock64();
+      int n_w2 = 0;
+      auto g1 = [&](int i, const FlowTile& t) {
+        const int buf = i & 1;
+        const uint32_t d = tmem_base + buf * 128;
+        const int resid_chunk = 6 + t.r % 3;       // centre tap (chunks 6..8), ring slot of the newest row
+        for (int j = 0; j < kChunks; ++j, ++it) {
+          const int s = it % kStages;
+          PK_TICK(0)
+          mbar_wait_a(full_bar + 8 * s, (it / kStages) & 1);
+          PK_TICK(1)
+          tcgen05_fence_after();
+          const uint32_t st = smem + s * kStageBytes;
+          const uint64_t a_hi = make_smem_desc_sw128(st), a_lo = make_smem_desc_sw128(st + kATile);
+          const uint64_t b_hi = make_smem_desc_sw128(st + 2 * kATile), b_lo = make_smem_desc_sw128(st + 2 * kATile + kWTile);
+          const int ksteps = j == kChunks - 1 ? p.cond_ksteps_last : 4;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16_2sm(d, a_hi + koff, b_hi + koff, idesc, !(j == 0 && k == 0));
+            umma_bf16_2sm(d, a_lo + koff, b_hi + koff, idesc, 1);
+            umma_bf16_2sm(d, a_hi + koff, b_lo + koff, idesc, 1);
+          }
+          if (j == resid_chunk) {
+            mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
+            PK_TICK(2)
+            tcgen05_fence_after();
+            const uint64_t b_id = make_smem_desc_sw128(ident);
+            const uint32_t d2 = tmem_base + 256 + buf * 128;
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+              umma_bf16_2sm(d2, a_hi + koff, b_id + koff, idesc, k != 0);
+              umma_bf16_2sm(d2, a_lo + koff, b_id + koff, idesc, 1);
+            }
+          }
+          umma_commit_2sm_a(empty_bar + 8 * s);
+        }
+        umma_commit_2sm_a(acc1_full + 8 * buf);
+      };
+      auto g2 = [&](int i, bool new_w2, bool release_w2) {
+        const int buf = i & 1;
+        PK_TICK(0)
+        if (new_w2) {
+          mbar_wait_a(w2_full, n_w2 & 1);
+          ++n_w2;
+        }
+        mbar_wait_a(z_full + 8 * buf, (i >> 1) & 1);
+        PK_TICK(3)
+        tcgen05_fence_after();
+        const uint32_t za = tmem_base + buf * 128;
+        const uint32_t d2 = tmem_base + 256 + buf * 128;
+        const uint64_t b_hi = make_smem_desc_sw128(w2), b_lo = make_smem_desc_sw128(w2 + kWTile);
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+          const uint32_t a_hi = za + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
+          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, 1);
+          umma_bf16_2sm_ts(d2, a_lo, b_hi + koff, idesc, 1);
+          umma_bf16_2sm_ts(d2, a_hi, b_lo + koff, idesc, 1);
+        }
+        if (release_w2) umma_commit_2sm_a(w2_empty);   // the next tile belongs to another step: its out_proj may replace this one
+        umma_commit_2sm_a(acc2_full + 8 * buf);
+      };
+      FlowTile cur, nxt;
+      int T = pair;
+      bool have = T < p.total_tiles;
+      int i = 0;
+      bool cur_new = true;
+      if (have) {
+        cur.decode(p, T);
+        g1(0, cur);
+      }
+      while (have) {
+        const int Tn = T + n_pairs;
+        const bool have_next = Tn < p.total_tiles;
+        bool next_new = false;
+        if (have_next) {
+          nxt.decode(p, Tn);
+          next_new = nxt.s != cur.s;
+          if (!p.serial) g1(i + 1, nxt);           // GEMM1 of the next tile covers the gate warps' latency on this one
+        }
+        g2(i, cur_new, have_next && next_new);
+        if (have_next && p.serial) g1(i + 1, nxt);
+        cur = nxt; cur_new = next_new; T = Tn; have = have_next; ++i;
+      }
+      PK_TICK(0)
+      if (kProf) {
+        for (int k = 0; k < 4; ++k) atomicAdd(p.prof + k, static_cast<unsigned long long>(tacc[k]));
+        atomicAdd(p.prof + 4, static_cast<unsigned long long>(i));
+      }
+    }
+  } else if (warp < kFirstGateWarp) {
+    // idle warps
+  } else if (warp < kFirstGateWarp + kGateWarps) {
+    // ------------------------------ gate warps (both CTAs, own TMEM lanes) ------------------------------
+    const int quarter = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t z_full_l = mapa_shared(z_full, 0);
+    float k_a, k_g;
+    asm volatile("mov.f32 %0, %2;\n\tmov.f32 %1, %3;" : "=f"(k_a), "=f"(k_g) : "f"(p.k_a), "f"(p.k_g));
+    FlowTile t;
+    int i = 0;
+    for (int T = pair; T < p.total_tiles; T += n_pairs, ++i) {
+      t.decode(p, T);
+      const float* gc = p.gate_c[t.l];
+      const int buf = i & 1;
+      mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t acc = tmem_base + lane_base + buf * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float va[32], vb[32];
+        uint32_t zw[32];
+        __syncwarp();
+        tmem_ld_32x32(acc + half * 32, va);
+        tmem_ld_32x32(acc + 64 + half * 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float zz[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float e1 = ex2_approx(fminf(fmaf(va[j + e], k_a, gc[half * 32 + j + e]), 60.f));
+            const float e2 = ex2_approx(fminf(fmaf(vb[j + e], k_g, gc[64 + half * 32 + j + e]), 60.f));
+            const float t1 = 1.f + e1;
+            zz[e] = (1.f - e1) * rcp_approx(fmaf(t1, e2, t1));
+          }
+          split2(zz[0], zz[1], zw[j / 2], zw[16 + j / 2]);
+          split2(zz[2], zz[3], zw[j / 2 + 1], zw[16 + j / 2 + 1]);
+        }
+        tmem_st_32x32(acc + half * 32, zw);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed_a(z_full_l + 8 * buf);
+    }
+  } else {
+    // ------------------------------ store warps (both CTAs) ------------------------------
+    const int sw = warp - kFirstGateWarp - kGateWarps;
+    const int quarter = warp & 3;
+    const int half = sw >> 2;                 // 0: skip columns [0, 64), 1: new row columns [64, 128)
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t acc2_empty_l = mapa_shared(acc2_empty, 0);
+    FlowTile t;
+    int i = 0;
+    for (int T = pair; T < p.total_tiles; T += n_pairs, ++i) {
+      t.decode(p, T);
+      const int buf = i & 1;
+      const int row = t.m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
+      const long long pos = static_cast<long long>(t.b) * p.w + row;
+      const bool last_layer = t.l == p.n_layers - 1;
+      const bool live = row < p.w;
+      const float* ob = p.out_b[t.l] + half * 64;
+      mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
+      tcgen05_fence_after();
+      const bool idle = half == 1 && last_layer;       // the residual half of the last layer feeds nothing
+      float v[64];
+      __syncwarp();
+      if (!idle) {
+        // both halves of this warp's 64 columns first, so that the accumulator goes back to the issuer before any store
+        tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64, v);
+        tmem_ld_32x32(tmem_base + lane_base + 256 + buf * 128 + half * 64 + 32, v + 32);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l + 8 * buf);
+      if (idle || !live) {
+        // nothing to store: the last layer's residual half, or positions past the end of the row
+      } else if (half == 0) {
+        float* dst = p.skip + pos * kC;
+        float s0 = 0.f, s1 = 0.f;                        // output_proj (last layer)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 o = make_float4(v[4 * c] + ob[4 * c], v[4 * c + 1] + ob[4 * c + 1], v[4 * c + 2] + ob[4 * c + 2],
+                                 v[4 * c + 3] + ob[4 * c + 3]);
+          if (last_layer) {
+            // the sum of the skips is complete here: output_proj in registers instead of a last read-modify-write
+            if (p.n_layers > 1) {
+              const float4 a = ld_cg_f4(dst + 4 * c);
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            const float* w0 = p.po_w + 4 * c;
+            s0 = fmaf(w0[0], o.x, fmaf(w0[1], o.y, fmaf(w0[2], o.z, fmaf(w0[3], o.w, s0))));
+            s1 = fmaf(w0[kC], o.x, fmaf(w0[kC + 1], o.y, fmaf(w0[kC + 2], o.z, fmaf(w0[kC + 3], o.w, s1))));
+          } else if (t.l == 0) {
+            *reinterpret_cast<float4*>(dst + 4 * c) = o;
+          } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+        }
+        if (last_layer) {
+          // Flow._inverse_transform_row (:505-510) and, for the next row step, Flow.input_proj (:437-442) into layer 0's ring
+          const int irow = t.r + 1;
+          const long long xi = (static_cast<long long>(t.b) * p.n_group + irow) * p.w + row;
+          const float logs = s0 + p.po_b[0], bb = s1 + p.po_b[1];
+          const float xn = (__ldg(p.z + xi) - bb) * expf(-logs);
+          p.x[xi] = xn;
+          if (irow + 1 < p.n_group) {
+            const long long off = pos * (3 * kC) + (irow % 3) * kC;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t oh[8], ol[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = 16 * q + 2 * e;
+                split2(fmaf(p.in_w[c], xn, p.in_b[c]), fmaf(p.in_w[c + 1], xn, p.in_b[c + 1]), oh[e], ol[e]);
+              }
+              st_global_v8(p.ring_hi[0] + off + 16 * q, oh);
+              st_global_v8(p.ring_lo[0] + off + 16 * q, ol);
+            }
+          }
+        }
+      } else {
+        const long long off = pos * (3 * kC) + (t.r % 3) * kC;
+        __nv_bfloat16* yh = p.ring_hi[t.l + 1];
+        __nv_bfloat16* yl = p.ring_lo[t.l + 1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t oh[8], ol[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = 16 * q + 2 * e;
+            split2(v[c] + ob[c], v[c + 1] + ob[c + 1], oh[e], ol[e]);
+          }
+          st_global_v8(yh + off + 16 * q, oh);
+          st_global_v8(yl + off + 16 * q, ol);
+        }
+      }
+      // publish the tile: this warp's rows are written (generic proxy) -> visible to the async-proxy reads of the consumers
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async_all();
+        __threadfence();
+        red_release_gpu_inc(p.flags + T);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
 }  // namespace wf
 }  // namespace pk
 
@@ -439,6 +890,98 @@ extern "C" int pk_waveflow_layer(const pk_waveflow_layer_args* a, pk_stream_t st
     waveflow_layer_kernel<true><<<grid, kThreads, kSmem, st>>>(tx, tc, tw1, tw2_hi, tw2_lo, p);
   } else {
     waveflow_layer_kernel<false><<<grid, kThreads, kSmem, st>>>(tx, tc, tw1, tw2_hi, tw2_lo, p);
+  }
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
+extern "C" int pk_waveflow_flow(const pk_waveflow_flow_args* a, pk_stream_t stream) {
+  using namespace pk;
+  using namespace pk::wf;
+  PK_CHECK_ARG(a != nullptr, "args is NULL");
+  PK_CHECK_ARG(a->batch > 0 && a->width > 0, "bad batch/width");
+  PK_CHECK_ARG(a->channels == kC, "the fused WaveFlow flow is built for 64 residual channels (got %d)", a->channels);
+  PK_CHECK_ARG(a->n_mels > 64 && a->n_mels <= 128 && (a->n_mels % 8) == 0, "n_mels must be in (64, 128], a multiple of 8");
+  PK_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= kMaxLayers && a->n_group >= 2 && a->n_group <= kMaxGroup,
+               "n_layers must be 1..8 (width dilation 2^l <= 128) and n_group 2..16");
+  PK_CHECK_ARG(a->cond_rows && a->ring_hi && a->ring_lo && a->cond_hi && a->cond_lo && a->w1_hi && a->w1_lo && a->w2_hi && a->w2_lo &&
+               a->bias1 && a->bias2 && a->in_w && a->in_b && a->out_w && a->out_b && a->z && a->x && a->skip && a->flags,
+               "NULL pointer in pk_waveflow_flow_args");
+  static int max_pairs = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(waveflow_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(waveflow_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    // every pair must be resident at once (tiles wait for tiles of other pairs): ask the driver how many clusters of 2 fit
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    PK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, waveflow_flow_kernel<false>, &cfg));
+    PK_CHECK_ARG(n >= 1, "no resident CTA pair available for pk_waveflow_flow");
+    max_pairs = std::min(n, sm_count() / 2);
+    attr_set = true;
+  }
+  static FlowArgs p;       // 14 KB of kernel parameters: built in place (host calls are serialised by the Python layer)
+  const uint64_t W = a->width, B = a->batch;
+  int rc;
+  for (int l = 0; l < a->n_layers; ++l) {
+    PK_CHECK_ARG(a->ring_hi[l] && a->ring_lo[l] && a->w2_hi[l] && a->w2_lo[l] && a->bias1[l] && a->bias2[l], "NULL entry for layer %d", l);
+    if ((rc = encode_tmap_bf16_planes(&p.tm_x[l], a->ring_hi[l], a->ring_lo[l], 3 * kC, W, B, 3 * kC, W * 3 * kC, 128))) return rc;
+    for (int v = 0; v < 3; ++v) {
+      PK_CHECK_ARG(a->w1_hi[3 * l + v] && a->w1_lo[3 * l + v], "NULL GEMM1 weight for layer %d variant %d", l, v);
+      if ((rc = encode_tmap_bf16_planes(&p.tm_w1[l][v], a->w1_hi[3 * l + v], a->w1_lo[3 * l + v], kW1Cols, kG, 1, kW1Cols, 0, 64))) return rc;
+    }
+    if ((rc = encode_tmap_bf16_planes(&p.tm_w2[l], a->w2_hi[l], a->w2_lo[l], 64, kG, 1, 64, 0, 64))) return rc;
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int i = 0; i < 64; ++i) {
+      p.gate_c[l][i] = -2.f * kLog2e * a->bias1[l][i];
+      p.gate_c[l][64 + i] = -kLog2e * a->bias1[l][64 + i];
+    }
+    for (int i = 0; i < 128; ++i) p.out_b[l][i] = a->bias2[l][i];
+    p.ring_hi[l] = static_cast<__nv_bfloat16*>(a->ring_hi[l]);
+    p.ring_lo[l] = static_cast<__nv_bfloat16*>(a->ring_lo[l]);
+  }
+  if ((rc = encode_tmap_bf16_planes(&p.tm_c, a->cond_hi, a->cond_lo, a->n_mels, W, B * a->n_group, a->n_mels, W * a->n_mels, 128)))
+    return rc;
+  p.batch = a->batch; p.w = a->width; p.n_layers = a->n_layers; p.n_group = a->n_group; p.n_rows = a->n_group - 1;
+  p.tiles_per_b = (a->width + 255) / 256;
+  p.tiles_per_step = p.tiles_per_b * a->batch;
+  const long long total = static_cast<long long>(p.tiles_per_step) * p.n_rows * p.n_layers;
+  PK_CHECK_ARG(total < (1ll << 30) && a->flags_len >= total, "flags must hold one counter per tile (%lld)", total);
+  p.total_tiles = static_cast<int>(total);
+  p.cond_ksteps_last = (a->n_mels - 64 + kUmmaK - 1) / kUmmaK;
+  for (int i = 0; i < a->n_group; ++i) {
+    PK_CHECK_ARG(a->cond_rows[i] >= 0 && a->cond_rows[i] < a->n_group, "cond_rows[%d] out of range", i);
+    p.cmap[i] = a->cond_rows[i];
+  }
+  for (int i = 0; i < kC; ++i) { p.in_w[i] = a->in_w[i]; p.in_b[i] = a->in_b[i]; p.po_w[i] = a->out_w[i]; p.po_w[kC + i] = a->out_w[kC + i]; }
+  p.po_b[0] = a->out_b[0]; p.po_b[1] = a->out_b[1];
+  constexpr float kLog2e = 1.4426950408889634f;
+  p.k_a = -2.f * kLog2e; p.k_g = -kLog2e;
+  p.skip = a->skip; p.z = a->z; p.x = a->x; p.flags = a->flags;
+  p.prof = static_cast<unsigned long long*>(a->prof);
+  // GEMM2 of tile i is issued after GEMM1 of the pair's next tile i + n_pairs, which waits for tiles up to
+  // i + n_pairs - tiles_per_step + 1: that must stay below i, or the pair waits for itself.  Tiny problems run unpipelined.
+  const int reach = p.tiles_per_b > 1 ? 1 : 0;
+  int n_pairs = std::min(max_pairs, p.tiles_per_step - 1 - reach);
+  p.serial = 0;
+  if (n_pairs < 1) {
+    n_pairs = std::min(max_pairs, p.tiles_per_step);
+    p.serial = 1;
+  }
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.prof != nullptr) {
+    waveflow_flow_kernel<true><<<2 * n_pairs, kThreads, kSmem, st>>>(p);
+  } else {
+    waveflow_flow_kernel<false><<<2 * n_pairs, kThreads, kSmem, st>>>(p);
   }
   PK_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -134,7 +134,10 @@ class ConditionalWaveFlow(Layer):
             # the condition projections of all layers of a flow in one GEMM per row step (they do not depend on the recurrence)
             cond_w = torch.cat([p[f"{pre}resnet.{l}.condition_proj.weight"][:, :, 0, 0] for l in range(self.n_layers)], dim=0)
             cond_b = torch.cat([p[f"{pre}resnet.{l}.condition_proj.bias"] for l in range(self.n_layers)])
-            pk["flows"].append(dict(in_w=p[pre + "input_proj.weight"].reshape(-1).contiguous().to(dev),
+            f32 = lambda t: t.detach().float().contiguous().numpy().astype("float32").copy()
+            host = dict(in_w=f32(p[pre + "input_proj.weight"].reshape(-1)), in_b=f32(p[pre + "input_proj.bias"]),
+                        out_w=f32(p[pre + "output_proj.weight"].reshape(2, C)), out_b=f32(p[pre + "output_proj.bias"]))
+            pk["flows"].append(dict(host=host, in_w=p[pre + "input_proj.weight"].reshape(-1).contiguous().to(dev),
                                     in_b=p[pre + "input_proj.bias"].to(dev), layers=layers,
                                     cond_all=ops.pack_weight(cond_w, dev), cond_all_b=cond_b.contiguous().to(dev),
                                     out_w=p[pre + "output_proj.weight"].reshape(2, C).contiguous().to(dev),
@@ -144,10 +147,38 @@ class ConditionalWaveFlow(Layer):
         return pk
 
     def _fusable(self):
-        """pk_waveflow_layer (one kernel per ResidualBlock.add_input) covers 64 residual channels and 64 < n_mels <= 128;
-        PK_WF_FUSED=0 keeps the two-GEMM path for A/B runs."""
+        """The fused kernels (pk_waveflow_flow: one persistent launch per flow; pk_waveflow_layer: one launch per
+        ResidualBlock.add_input) cover 64 residual channels and 64 < n_mels <= 128.  PK_WF_FUSED=layer selects the per-layer
+        kernel, PK_WF_FUSED=0 the two-GEMM path (A/B runs)."""
         return (self.channels == 64 and 64 < self.n_mels <= 128 and self.n_mels % 8 == 0
                 and os.environ.get("PK_WF_FUSED", "1") != "0")
+
+    def _flow_mode(self):
+        return self._fusable() and self.n_layers <= 8 and os.environ.get("PK_WF_FUSED", "1") != "layer"
+
+    def _run_flow(self, fw, z, x, cond_s, cmap, bufs, skip, flags, prof, st):
+        """Rows 1 .. G-1 of one flow in one launch (row 0 and the ring contents are prepared by the caller)."""
+        L = _lib.lib()
+        B, G, W = z.shape
+        NL = self.n_layers
+        lay = [l_["fused"] for l_ in fw["layers"]]
+        vpa = lambda ptrs: (C_.c_void_p * len(ptrs))(*ptrs)
+        keep = dict(cond_rows=(C_.c_int32 * G)(*cmap), ring_hi=vpa([_ptr(b_.hi) for b_ in bufs]), ring_lo=vpa([_ptr(b_.lo) for b_ in bufs]),
+                    w1_hi=vpa([_ptr(f["w1"][v][0]) for f in lay for v in range(3)]),
+                    w1_lo=vpa([_ptr(f["w1"][v][1]) for f in lay for v in range(3)]),
+                    w2_hi=vpa([_ptr(f["w2"][0]) for f in lay]), w2_lo=vpa([_ptr(f["w2"][1]) for f in lay]),
+                    bias1=vpa([f["b1"].ctypes.data for f in lay]), bias2=vpa([f["b2"].ctypes.data for f in lay]))
+        a = _lib.WaveflowFlowArgs()
+        a.batch, a.width, a.channels, a.n_mels, a.n_layers, a.n_group = B, W, self.channels, self.n_mels, NL, G
+        for k, v in keep.items():
+            setattr(a, k, C_.cast(v, C_.c_void_p))
+        a.cond_hi, a.cond_lo = _ptr(cond_s.hi), _ptr(cond_s.lo)
+        h = fw["host"]
+        a.in_w, a.in_b, a.out_w, a.out_b = (h[k].ctypes.data for k in ("in_w", "in_b", "out_w", "out_b"))
+        a.z, a.x, a.skip, a.flags, a.flags_len = _ptr(z), _ptr(x), _ptr(skip), _ptr(flags), flags.numel()
+        if prof is not None:
+            a.prof = _ptr(prof)
+        _lib.check(L.pk_waveflow_flow(C_.byref(a), st), "pk_waveflow_flow")
 
     def encode(self, mel, trim_conv_artifact=True):
         """UpsampleNet.forward (:103-132): (B, n_mels, T') -> (B, n_mels, T)."""
@@ -183,6 +214,8 @@ class ConditionalWaveFlow(Layer):
         bufs = [Split.zeros((B, W, 3 * C), dev) for _ in range(NL)]
         st = _stream()
         fused = self._fusable()
+        flow_mode = self._flow_mode()
+        flags = torch.empty((G - 1) * NL * B * ((W + 255) // 256), dtype=torch.int32, device=dev) if flow_mode else None
         prof = getattr(self, "_prof", None)                                               # debug: device uint64[8] phase counters
         for fi in reversed(range(self.n_flows)):
             perm = self.perms[fi]
@@ -194,6 +227,15 @@ class ConditionalWaveFlow(Layer):
             for b_ in bufs:
                 b_.hi.zero_()
                 b_.lo.zero_()
+            if flow_mode:
+                z = z.contiguous()
+                _lib.check(L.pk_waveflow_input_proj(_ptr(x[:, 0]), G * W, _ptr(fw["in_w"]), _ptr(fw["in_b"]), B, W, C,
+                                                    _ptr(state), _ptr(bufs[0].hi), _ptr(bufs[0].lo), 3 * C, 0, st),
+                           "pk_waveflow_input_proj")
+                flags.zero_()
+                self._run_flow(fw, z, x, cond_s, cmap, bufs, skip, flags, prof, st)
+                z = x
+                continue
             for i in range(1, G):
                 slot = (i - 1) % 3                                                        # ring slot of the newest row (row i-1)
                 _lib.check(L.pk_waveflow_input_proj(_ptr(x[:, i - 1]), G * W, _ptr(fw["in_w"]), _ptr(fw["in_b"]), B, W, C,
