@@ -506,7 +506,7 @@ def main():
             torch.cuda.synchronize()
             wf_ms = e0.elapsed_time(e1) / 3
             out["extra"]["waveflow_b16_c64"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
-                                                "note": "cfg4; one CUDA graph per call (fused GEMM epilogues)"}
+                                                "note": "cfg4; one persistent dataflow launch per flow (pk_waveflow_flow), one CUDA graph per call"}
             # Parallel WaveGAN training step (the workload of the reference's own benchmark harness, tests/benchmark/PWGAN/
             # run_benchmark.sh: batch 6, batch_max_steps 25 500, metric sequences/s), past discriminator_train_start_steps: generator
             # step with the adversarial term + discriminator step

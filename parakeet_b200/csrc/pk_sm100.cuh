@@ -298,12 +298,6 @@ __device__ __forceinline__ void tma_load_4d_2sm_a(uint32_t smem_dst, const CUten
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// L2 prefetch of one box of a 4-D tensor map (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0),
-               "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm_a(uint32_t smem_result) {   // one whole warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "n"(kCols) : "memory");

@@ -535,56 +535,26 @@ waveflow_flow_kernel(const __grid_constant__ FlowArgs p) {
         tma_load_4d_2sm_a(w2, &p.tm_w2[l], w2_full_leader, 0, 64 * static_cast<int>(rank), 0, 0);
         ++n_w2;
       };
-      FlowTile t, tn;
-      bool ready_ahead = false;  // the dependencies of this tile were already seen complete while the previous tile was loading
-      auto deps_done = [&](const FlowTile& q, int tq) {
-        // three independent acquire loads in flight at once; tiles mt-1 .. mt+1 of the previous step
-        const unsigned* f = p.flags + (tq - p.tiles_per_step);
-        const unsigned a = q.mt > 0 ? ld_acquire_gpu(f - 1) : kTileDone;
-        const unsigned b = ld_acquire_gpu(f);
-        const unsigned c = q.mt + 1 < p.tiles_per_b ? ld_acquire_gpu(f + 1) : kTileDone;
-        return a >= kTileDone && b >= kTileDone && c >= kTileDone;
-      };
+      FlowTile t;
       for (int T = pair; T < p.total_tiles; T += n_pairs) {
         t.decode(p, T);
         if (t.s > 0) {
           // the rows this tile reads were written by tiles mt-1 .. mt+1 of the previous step (other pairs, generic-proxy stores)
-          if (!ready_ahead && !deps_done(t, T)) {
+          const unsigned* f = p.flags + (T - p.tiles_per_step);
+          const bool lo = t.mt > 0, hi = t.mt + 1 < p.tiles_per_b;
+          const bool ready = (!lo || ld_acquire_gpu(f - 1) >= kTileDone) && ld_acquire_gpu(f) >= kTileDone &&
+                             (!hi || ld_acquire_gpu(f + 1) >= kTileDone);
+          if (!ready) {
             // a tile this one waits for may be the pair's own previous tile, which cannot finish without its out_proj
             if (pend >= 0) {
               load_w2(pend);
               pend = -1;
             }
-            const unsigned* f = p.flags + (T - p.tiles_per_step);
-            if (t.mt > 0) wait_tile_done(f - 1);
+            if (lo) wait_tile_done(f - 1);
             wait_tile_done(f);
-            if (t.mt + 1 < p.tiles_per_b) wait_tile_done(f + 1);
+            if (hi) wait_tile_done(f + 1);
           }
           fence_proxy_async_all();       // ... and are read here through the async proxy
-        }
-        ready_ahead = false;
-        const int Tn = T + n_pairs;
-        const bool have_next = Tn < p.total_tiles;
-        if (have_next) {
-          // the two older ring slots of the next tile were written a whole row step ago (1.5 GB of traffic: gone from L2):
-          // start their HBM reads one tile ahead.  (L2 is the point of coherence: a line prefetched early is not stale.)
-          tn.decode(p, Tn);
-          const int rown = tn.m0 + 128 * static_cast<int>(rank);
-          const int newest = tn.r % 3;
-#pragma unroll
-          for (int sl = 0; sl < 3; ++sl) {
-            if (sl == newest) continue;
-#pragma unroll
-            for (int tap = 0; tap < 3; ++tap) {
-              if (tap == 1 && tn.l < 7) continue;      // dilation < 128: the centre rows are covered by the outer taps' boxes
-              tma_prefetch_l2_4d(&p.tm_x[tn.l], sl * kC, rown + (tap - 1) * (1 << tn.l), tn.b, 0);
-            }
-          }
-          if (tn.l == 0) {                             // a new condition row: the later layers of the row step find it in L2
-            const int crown = tn.b * p.n_group + p.cmap[tn.r + 1];
-            tma_prefetch_l2_4d(&p.tm_c, 0, rown, crown, 0);
-            tma_prefetch_l2_4d(&p.tm_c, kChunkK, rown, crown, 0);
-          }
         }
         const int row0 = t.m0 + 128 * static_cast<int>(rank);
         const int variant = (t.r + 1) % 3;                     // row step i = r + 1
@@ -597,7 +567,6 @@ waveflow_flow_kernel(const __grid_constant__ FlowArgs p) {
             load_w2(pend);
             pend = -1;
           }
-          if (j == 7 && have_next && tn.s > 0) ready_ahead = deps_done(tn, Tn);   // off the critical path: the ring is full here
           const uint32_t st = smem + s * kStageBytes;
           const uint32_t fb = full_leader + 8 * s;
           if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kStageBytes);

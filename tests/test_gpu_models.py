@@ -240,6 +240,49 @@ def test_waveflow_wide_rows_vs_oracle(cuda):
     assert list(out.shape) == list(ref.shape) and rel_err(out, ref) < TOL
 
 
+@pytest.mark.parametrize("mode", ["layer", "0"])
+def test_waveflow_layer_paths_agree(cuda, monkeypatch, mode):
+    """The per-layer fused kernel (PK_WF_FUSED=layer) and the two-GEMM path (PK_WF_FUSED=0) stay parity-green: they are the
+    A/B baselines of the persistent flow kernel (default) and the fallback for channel counts it does not cover."""
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    params = owf.synth_params(4)
+    folded = owf.fold_weight_norm(params)
+    g = torch.Generator().manual_seed(43)
+    mel = torch.randn(2, 80, 20, generator=g) * 0.5 - 3
+    z = torch.randn(2, 256 * 20 - 272, generator=g)
+    with torch.no_grad():
+        ref = owf.infer(folded, mel, z)
+    monkeypatch.setenv("PK_WF_FUSED", mode)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m.set_state_dict(params)
+    out = m.infer(mel.to(cuda), z=z.to(cuda))
+    assert rel_err(out, ref) < TOL
+    monkeypatch.setenv("PK_WF_FUSED", "1")
+    m2 = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m2.set_state_dict(params)
+    assert rel_err(m2.infer(mel.to(cuda), z=z.to(cuda)), out) < 1e-4
+
+
+def test_waveflow_flow_kernel_single_utterance_and_edges(cuda):
+    """pk_waveflow_flow scheduling corners: one utterance with a single tile per step (every tile depends on the pair's own
+    previous tile: unpipelined issue order), two tiles per step, and a width just past a tile boundary (257 columns)."""
+    from oracle import waveflow as owf
+    from parakeet_b200.models import ConditionalWaveFlow
+    params = owf.synth_params(4)
+    folded = owf.fold_weight_norm(params)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m.set_state_dict(params)
+    for batch, frames, seed in ((1, 9, 51), (1, 18, 52), (2, 18, 53)):     # W = 127, 271, 271
+        g = torch.Generator().manual_seed(seed)
+        mel = torch.randn(batch, 80, frames, generator=g) * 0.5 - 3
+        z = torch.randn(batch, 256 * frames - 272, generator=g)
+        with torch.no_grad():
+            ref = owf.infer(folded, mel, z)
+        out = m.infer(mel.to(cuda), z=z.to(cuda))
+        assert rel_err(out, ref) < TOL, (batch, frames)
+
+
 def test_waveflow_cfg4_full_size_properties(cuda):
     """cfg4 (B=16, 400 mel frames -> 16 x 102 128 samples, W = 6383): batch independence bit for bit, determinism / graph
     replay == eager, and one whole utterance against the oracle (mirror of test_pwg_full_size_properties)."""
