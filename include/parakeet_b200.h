@@ -372,7 +372,7 @@ typedef struct pk_waveflow_layer_args {
 int pk_waveflow_layer(const pk_waveflow_layer_args* args, pk_stream_t stream);
 
 /* All row steps i = 1 .. n_group-1 of one Flow.inverse (:515-556) in ONE persistent dataflow launch (the default path of
- * ConditionalWaveFlow.inverse for 64 channels; PK_WF_FUSED=layer selects one pk_waveflow_layer launch per layer and row).
+ * ConditionalWaveFlow.inverse for 64 and 128 channels; PK_WF_FUSED=layer selects one pk_waveflow_layer launch per layer and row).
  * Per row step: the n_layers ResidualBlock.add_input of pk_waveflow_layer, then on the completed skip sum
  * (logs, b) = output_proj(skip), x[:, i] = (z[:, i] - b) exp(-logs) (:496-510) and input_proj(x[:, i]) (:437-442) into the
  * first layer's ring slot i mod 3.  The caller provides row 0: x[:, 0] = z[:, 0], input_proj(x[:, 0]) in slot 0 of ring 0
@@ -380,7 +380,11 @@ int pk_waveflow_layer(const pk_waveflow_layer_args* args, pk_stream_t stream);
  * batch * ceil(width / 256)) zeroed.  z / x: fp32 (batch, n_group, width).  cond planes (batch, n_group, width, n_mels);
  * cond_rows[i] (HOST) = the condition row used at row step i.  ring / w1 / w2 / bias1 / bias2: HOST arrays indexed by layer
  * (w1: 3 * layer + variant, variant = i mod 3) of the per-layer pointers of pk_waveflow_layer_args (biases: HOST floats).
- * in_w / in_b [64], out_w [2][64], out_b [2]: HOST floats. */
+ * in_w / in_b [channels], out_w [2][channels], out_b [2]: HOST floats.
+ * channels == 128 (examples/waveflow/config.py) runs the same dataflow with the channels as two blocks of 64: ring planes
+ * (batch, width, 384) with slot s in columns [128 s, 128 s + 128); w1 planes (256, 1280): rows a0 | g0 | a1 | g1 (64 each: gate
+ * channel a_k = conv output 64 k + c, g_k = 128 + 64 k + c), columns [128 (3 tap + s) + c] conv, [1152 + m] condition_proj;
+ * w2 planes (256, 128): rows skip0 | res0 | skip1 | res1; bias1 / bias2 [256] in the same row orders; skip (batch, width, 128). */
 typedef struct pk_waveflow_flow_args {
   int32_t batch, width, channels, n_mels, n_layers, n_group;
   const int32_t* cond_rows;

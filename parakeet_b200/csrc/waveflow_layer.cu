@@ -836,6 +836,386 @@ waveflow_flow_kernel(const __grid_constant__ FlowArgs p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// 128 residual channels (examples/waveflow/config.py): the same dataflow over tiles, with the channel dimension as TWO blocks
+// of 64.  Gate channels are ordered a0 | g0 | a1 | g1 (64 each) and out_proj rows skip0 | res0 | skip1 | res1, so one N = 256
+// MMA fills both blocks and the gate / store warps run the 64-channel code once per block.  Both accumulators take 256
+// columns each: they are single-buffered and a pair finishes tile i (GEMM1 -> gate -> GEMM2) before it starts tile i + 1 -
+// GEMM1 alone is 240 MMAs here, the exposed gate latency is ~10 % of a tile.  K = 9 x 128 + 80: 20 chunks of GEMM1, each
+// stage = A chunk (32 KB) + this CTA's 128 rows of the weight chunk (32 KB), 3 stages; out_proj (K = 128) follows as two
+// weight-only chunks through the same ring.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace c128 {
+constexpr int kCh = 128;
+constexpr int kStages3 = 3;
+constexpr int kWBytes = 2 * kATile;                          // hi | lo of this CTA's 128 weight rows of one chunk
+constexpr int kStage = 2 * kATile + kWBytes;                 // 64 KB
+constexpr int kG1Chunks = 20;                                // 18 conv chunks + 2 condition chunks
+constexpr int kG2Chunks = 2;
+constexpr int kW1Cols128 = kG1Chunks * kChunkK;              // 1280
+constexpr int kSmem128 = kStages3 * kStage + kWTile + 1024 + 256;
+static_assert(kSmem128 <= 227 * 1024, "shared memory budget");
+
+struct Flow128Args {
+  CUtensorMap tm_x[kMaxLayers];          // ring planes (batch, w, 384)
+  CUtensorMap tm_w1[kMaxLayers][3];      // (256, 1280) planes, box 128 rows
+  CUtensorMap tm_w2[kMaxLayers];         // (256, 128) planes, box 128 rows
+  CUtensorMap tm_c;
+  int batch, w, n_layers, n_rows, n_group, tiles_per_b, tiles_per_step, total_tiles, cond_ksteps_last;
+  int cmap[kMaxGroup];
+  float gate_c[kMaxLayers][256];         // accumulator order a0 | g0 | a1 | g1, pre-scaled
+  float out_b[kMaxLayers][256];          // skip0 | res0 | skip1 | res1
+  float in_w[kCh], in_b[kCh];
+  float po_w[2 * kCh], po_b[2];
+  float k_a, k_g;
+  float* skip;                           // (batch, w, 128)
+  const float* z;
+  float* x;
+  __nv_bfloat16* ring_hi[kMaxLayers];
+  __nv_bfloat16* ring_lo[kMaxLayers];
+  unsigned* flags;
+};
+
+struct Tile128 {
+  int s, l, r, b, m0, mt;
+  __device__ void decode(const Flow128Args& p, int t) {
+    s = t / p.tiles_per_step;
+    const int rem = t - s * p.tiles_per_step;
+    r = s / p.n_layers;
+    l = s - r * p.n_layers;
+    b = rem / p.tiles_per_b;
+    mt = rem - b * p.tiles_per_b;
+    m0 = mt * 256;
+  }
+};
+
+// GEMM1 chunk j < 18 -> (tap, ring slot, channel half); the centre tap comes last (its newest-slot chunks feed the residual pass)
+__device__ __forceinline__ void chunk_of(int j, int& tap, int& slot, int& half) {
+  const int t3 = j / 6, rem = j - 6 * t3;
+  tap = t3 == 0 ? 0 : t3 == 1 ? 2 : 1;
+  slot = rem >> 1;
+  half = rem & 1;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+waveflow_flow128_kernel(const __grid_constant__ Flow128Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ident = smem + kStages3 * kStage;             // this CTA's 64 rows of [0 | I] (N = 128 residual pass)
+  const uint32_t bars = ident + kWTile;
+  const uint32_t full_bar = bars;                              // [3] leader
+  const uint32_t empty_bar = full_bar + 8 * kStages3;          // [3]
+  const uint32_t acc1_full = empty_bar + 8 * kStages3;
+  const uint32_t acc2_full = acc1_full + 8;
+  const uint32_t acc2_empty = acc2_full + 8;                   // leader
+  const uint32_t z_full = acc2_empty + 8;                      // leader
+  const uint32_t tmem_slot = z_full + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = static_cast<int>(blockIdx.x >> 1), n_pairs = static_cast<int>(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages3; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
+    mbar_init_a(acc1_full, 1);
+    mbar_init_a(acc2_full, 1);
+    mbar_init_a(acc2_empty, 2 * kStoreWarps);
+    mbar_init_a(z_full, 2 * kGateWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm_a<512>(tmem_slot);
+  if (threadIdx.x >= 128 && threadIdx.x < 192) {
+    const int n = threadIdx.x - 128;     // [0 | I] over the pair: rank 1's rows put channel n into column 64 + n of the block
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (rank == 1 && (n >> 3) == c) {
+        const uint32_t one = (n & 1) ? 0x3f800000u : 0x00003f80u;
+        const int wd = (n & 7) >> 1;
+        v.x = wd == 0 ? one : 0; v.y = wd == 1 ? one : 0; v.z = wd == 2 ? one : 0; v.w = wd == 3 ? one : 0;
+      }
+      sts_u4(ident + n * kSwizzleBytes + ((c ^ (n & 7)) * 16), v);
+    }
+    fence_proxy_async_all();
+  }
+  tcgen05_fence_before();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = lds_u32(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      uint32_t it = 0;
+      const uint32_t full_leader = mapa_shared(full_bar, 0);
+      Tile128 t;
+      for (int T = pair; T < p.total_tiles; T += n_pairs) {
+        t.decode(p, T);
+        if (t.s > 0) {
+          const unsigned* f = p.flags + (T - p.tiles_per_step);
+          if (t.mt > 0) wait_tile_done(f - 1);
+          wait_tile_done(f);
+          if (t.mt + 1 < p.tiles_per_b) wait_tile_done(f + 1);
+          fence_proxy_async_all();
+        }
+        const int row0 = t.m0 + 128 * static_cast<int>(rank);
+        const int variant = (t.r + 1) % 3;
+        const int crow = t.b * p.n_group + p.cmap[t.r + 1];
+        for (int j = 0; j < kG1Chunks + kG2Chunks; ++j, ++it) {
+          const int s = it % kStages3;
+          mbar_wait_a(empty_bar + 8 * s, ((it / kStages3) & 1) ^ 1);
+          const uint32_t st = smem + s * kStage;
+          const uint32_t fb = full_leader + 8 * s;
+          if (j < kG1Chunks) {
+            if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kStage);
+            if (j < 18) {
+              int tap, slot, half;
+              chunk_of(j, tap, slot, half);
+              tma_load_4d_2sm_a(st, &p.tm_x[t.l], fb, slot * kCh + half * kC, row0 + (tap - 1) * (1 << t.l), t.b, 0);
+              tma_load_4d_2sm_a(st + 2 * kATile, &p.tm_w1[t.l][variant], fb, ((3 * tap + slot) * 2 + half) * kChunkK,
+                                128 * static_cast<int>(rank), 0, 0);
+            } else {
+              tma_load_4d_2sm_a(st, &p.tm_c, fb, (j - 18) * kChunkK, row0, crow, 0);
+              tma_load_4d_2sm_a(st + 2 * kATile, &p.tm_w1[t.l][variant], fb, j * kChunkK, 128 * static_cast<int>(rank), 0, 0);
+            }
+          } else {
+            // out_proj K-chunk (channels of z block j - 20): weights only
+            if (leader) mbar_arrive_expect_tx_a(full_bar + 8 * s, 2 * kWBytes);
+            tma_load_4d_2sm_a(st + 2 * kATile, &p.tm_w2[t.l], fb, (j - kG1Chunks) * kChunkK, 128 * static_cast<int>(rank), 0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------ MMA issuer ------------------------------
+      constexpr uint32_t idesc256 = make_idesc_bf16_f32(256, 256);
+      constexpr uint32_t idesc128 = make_idesc_bf16_f32(256, 128);
+      uint32_t it = 0;
+      Tile128 t;
+      int i = 0;
+      for (int T = pair; T < p.total_tiles; T += n_pairs, ++i) {
+        t.decode(p, T);
+        const uint32_t d1 = tmem_base;               // acc1: a0 | g0 | a1 | g1
+        const uint32_t d2 = tmem_base + 256;         // acc2: skip0 | res0 | skip1 | res1
+        const int newest = t.r % 3;
+        for (int j = 0; j < kG1Chunks; ++j, ++it) {
+          const int s = it % kStages3;
+          mbar_wait_a(full_bar + 8 * s, (it / kStages3) & 1);
+          tcgen05_fence_after();
+          const uint32_t st = smem + s * kStage;
+          const uint64_t a_hi = make_smem_desc_sw128(st), a_lo = make_smem_desc_sw128(st + kATile);
+          const uint64_t b_hi = make_smem_desc_sw128(st + 2 * kATile), b_lo = make_smem_desc_sw128(st + 3 * kATile);
+          const int ksteps = j == kG1Chunks - 1 ? p.cond_ksteps_last : 4;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16_2sm(d1, a_hi + koff, b_hi + koff, idesc256, !(j == 0 && k == 0));
+            umma_bf16_2sm(d1, a_lo + koff, b_hi + koff, idesc256, 1);
+            umma_bf16_2sm(d1, a_hi + koff, b_lo + koff, idesc256, 1);
+          }
+          if (j >= 12 && j < 18) {
+            int tap, slot, half;
+            chunk_of(j, tap, slot, half);
+            if (slot == newest) {
+              // residual pass of channel block `half`: acc2 block = [0 | row_hi + row_lo] (this also clears the skip half)
+              if (half == 0) {
+                mbar_wait_a(acc2_empty, (i & 1) ^ 1);      // the store warps have read tile i-1
+                tcgen05_fence_after();
+              }
+              const uint64_t b_id = make_smem_desc_sw128(ident);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                umma_bf16_2sm(d2 + 128 * half, a_hi + koff, b_id + koff, idesc128, k != 0);
+                umma_bf16_2sm(d2 + 128 * half, a_lo + koff, b_id + koff, idesc128, 1);
+              }
+            }
+          }
+          umma_commit_2sm_a(empty_bar + 8 * s);
+        }
+        umma_commit_2sm_a(acc1_full);
+        mbar_wait_a(z_full, i & 1);                  // z of both blocks is in tensor memory (over the a-columns of acc1)
+        tcgen05_fence_after();
+        for (int kc = 0; kc < kG2Chunks; ++kc, ++it) {
+          const int s = it % kStages3;
+          mbar_wait_a(full_bar + 8 * s, (it / kStages3) & 1);
+          tcgen05_fence_after();
+          const uint32_t st = smem + s * kStage;
+          const uint64_t b_hi = make_smem_desc_sw128(st + 2 * kATile), b_lo = make_smem_desc_sw128(st + 3 * kATile);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            const uint32_t a_hi = d1 + 128 * kc + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
+            umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc256, 1);
+            umma_bf16_2sm_ts(d2, a_lo, b_hi + koff, idesc256, 1);
+            umma_bf16_2sm_ts(d2, a_hi, b_lo + koff, idesc256, 1);
+          }
+          umma_commit_2sm_a(empty_bar + 8 * s);
+        }
+        umma_commit_2sm_a(acc2_full);
+      }
+    }
+  } else if (warp < kFirstGateWarp) {
+    // idle warps
+  } else if (warp < kFirstGateWarp + kGateWarps) {
+    // ------------------------------ gate warps ------------------------------
+    const int quarter = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t z_full_l = mapa_shared(z_full, 0);
+    float k_a, k_g;
+    asm volatile("mov.f32 %0, %2;\n\tmov.f32 %1, %3;" : "=f"(k_a), "=f"(k_g) : "f"(p.k_a), "f"(p.k_g));
+    Tile128 t;
+    int i = 0;
+    for (int T = pair; T < p.total_tiles; T += n_pairs, ++i) {
+      t.decode(p, T);
+      mbar_wait_a(acc1_full, i & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        const float* gc = p.gate_c[t.l] + 128 * blk;
+        const uint32_t acc = tmem_base + lane_base + 128 * blk;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float va[32], vb[32];
+          uint32_t zw[32];
+          __syncwarp();
+          tmem_ld_32x32(acc + half * 32, va);
+          tmem_ld_32x32(acc + 64 + half * 32, vb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float zz[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float e1 = ex2_approx(fminf(fmaf(va[j + e], k_a, gc[half * 32 + j + e]), 60.f));
+              const float e2 = ex2_approx(fminf(fmaf(vb[j + e], k_g, gc[64 + half * 32 + j + e]), 60.f));
+              const float t1 = 1.f + e1;
+              zz[e] = (1.f - e1) * rcp_approx(fmaf(t1, e2, t1));
+            }
+            split2(zz[0], zz[1], zw[j / 2], zw[16 + j / 2]);
+            split2(zz[2], zz[3], zw[j / 2 + 1], zw[16 + j / 2 + 1]);
+          }
+          tmem_st_32x32(acc + half * 32, zw);
+        }
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed_a(z_full_l);
+    }
+  } else {
+    // ------------------------------ store warps ------------------------------
+    const int sw = warp - kFirstGateWarp - kGateWarps;
+    const int quarter = warp & 3;
+    const int half = sw >> 2;                 // 0: skip columns, 1: new row columns of each block
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t acc2_empty_l = mapa_shared(acc2_empty, 0);
+    Tile128 t;
+    int i = 0;
+    for (int T = pair; T < p.total_tiles; T += n_pairs, ++i) {
+      t.decode(p, T);
+      const int row = t.m0 + 128 * static_cast<int>(rank) + quarter * 32 + lane;
+      const long long pos = static_cast<long long>(t.b) * p.w + row;
+      const bool last_layer = t.l == p.n_layers - 1;
+      const bool live = row < p.w;
+      const bool idle = half == 1 && last_layer;
+      mbar_wait_a(acc2_full, i & 1);
+      tcgen05_fence_after();
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        const float* ob = p.out_b[t.l] + 128 * blk + 64 * half;
+        float v[64];
+        __syncwarp();
+        if (!idle) {
+          tmem_ld_32x32(tmem_base + lane_base + 256 + 128 * blk + 64 * half, v);
+          tmem_ld_32x32(tmem_base + lane_base + 256 + 128 * blk + 64 * half + 32, v + 32);
+          tmem_ld_wait();
+        }
+        if (blk == 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l);
+        }
+        if (idle || !live) {
+          // nothing to store
+        } else if (half == 0) {
+          float* dst = p.skip + pos * kCh + 64 * blk;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float4 o = make_float4(v[4 * c] + ob[4 * c], v[4 * c + 1] + ob[4 * c + 1], v[4 * c + 2] + ob[4 * c + 2],
+                                   v[4 * c + 3] + ob[4 * c + 3]);
+            if (last_layer) {
+              if (p.n_layers > 1) {
+                const float4 a = ld_cg_f4(dst + 4 * c);
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              const float* w0 = p.po_w + 64 * blk + 4 * c;
+              s0 = fmaf(w0[0], o.x, fmaf(w0[1], o.y, fmaf(w0[2], o.z, fmaf(w0[3], o.w, s0))));
+              s1 = fmaf(w0[kCh], o.x, fmaf(w0[kCh + 1], o.y, fmaf(w0[kCh + 2], o.z, fmaf(w0[kCh + 3], o.w, s1))));
+            } else if (t.l == 0) {
+              *reinterpret_cast<float4*>(dst + 4 * c) = o;
+            } else {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                           : "memory");
+            }
+          }
+        } else {
+          const long long off = pos * (3 * kCh) + (t.r % 3) * kCh + 64 * blk;
+          __nv_bfloat16* yh = p.ring_hi[t.l + 1];
+          __nv_bfloat16* yl = p.ring_lo[t.l + 1];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = 16 * q + 2 * e;
+              split2(v[c] + ob[c], v[c + 1] + ob[c + 1], oh[e], ol[e]);
+            }
+            st_global_v8(yh + off + 16 * q, oh);
+            st_global_v8(yl + off + 16 * q, ol);
+          }
+        }
+      }
+      if (half == 0 && last_layer && live) {
+        const int irow = t.r + 1;
+        const long long xi = (static_cast<long long>(t.b) * p.n_group + irow) * p.w + row;
+        const float logs = s0 + p.po_b[0], bb = s1 + p.po_b[1];
+        const float xn = (__ldg(p.z + xi) - bb) * expf(-logs);
+        p.x[xi] = xn;
+        if (irow + 1 < p.n_group) {
+          const long long off = pos * (3 * kCh) + (irow % 3) * kCh;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = 16 * q + 2 * e;
+              split2(fmaf(p.in_w[c], xn, p.in_b[c]), fmaf(p.in_w[c + 1], xn, p.in_b[c + 1]), oh[e], ol[e]);
+            }
+            st_global_v8(p.ring_hi[0] + off + 16 * q, oh);
+            st_global_v8(p.ring_lo[0] + off + 16 * q, ol);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async_all();
+        __threadfence();
+        red_release_gpu_inc(p.flags + T);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+}  // namespace c128
+
 }  // namespace wf
 }  // namespace pk
 
@@ -896,18 +1276,93 @@ extern "C" int pk_waveflow_layer(const pk_waveflow_layer_args* a, pk_stream_t st
   return PK_OK;
 }
 
+
+static int flow128_launch(const pk_waveflow_flow_args* a, pk_stream_t stream) {
+  using namespace pk;
+  using namespace pk::wf;
+  using namespace pk::wf::c128;
+  PK_CHECK_ARG(a->prof == nullptr, "no phase counters in the 128-channel flow kernel");
+  static int max_pairs = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PK_CHECK_CUDA(cudaFuncSetAttribute(waveflow_flow128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem128));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem128;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    PK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, waveflow_flow128_kernel, &cfg));
+    PK_CHECK_ARG(n >= 1, "no resident CTA pair available for pk_waveflow_flow");
+    max_pairs = std::min(n, sm_count() / 2);
+    attr_set = true;
+  }
+  static Flow128Args p;
+  const uint64_t W = a->width, B = a->batch;
+  int rc;
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (int l = 0; l < a->n_layers; ++l) {
+    PK_CHECK_ARG(a->ring_hi[l] && a->ring_lo[l] && a->w2_hi[l] && a->w2_lo[l] && a->bias1[l] && a->bias2[l], "NULL entry for layer %d", l);
+    if ((rc = encode_tmap_bf16_planes(&p.tm_x[l], a->ring_hi[l], a->ring_lo[l], 3 * kCh, W, B, 3 * kCh, W * 3 * kCh, 128))) return rc;
+    for (int v = 0; v < 3; ++v) {
+      PK_CHECK_ARG(a->w1_hi[3 * l + v] && a->w1_lo[3 * l + v], "NULL GEMM1 weight for layer %d variant %d", l, v);
+      if ((rc = encode_tmap_bf16_planes(&p.tm_w1[l][v], a->w1_hi[3 * l + v], a->w1_lo[3 * l + v], kW1Cols128, 256, 1, kW1Cols128, 0, 128)))
+        return rc;
+    }
+    if ((rc = encode_tmap_bf16_planes(&p.tm_w2[l], a->w2_hi[l], a->w2_lo[l], kCh, 256, 1, kCh, 0, 128))) return rc;
+    for (int blk = 0; blk < 2; ++blk) {
+      for (int i = 0; i < 64; ++i) {
+        p.gate_c[l][128 * blk + i] = -2.f * kLog2e * a->bias1[l][128 * blk + i];
+        p.gate_c[l][128 * blk + 64 + i] = -kLog2e * a->bias1[l][128 * blk + 64 + i];
+      }
+    }
+    for (int i = 0; i < 256; ++i) p.out_b[l][i] = a->bias2[l][i];
+    p.ring_hi[l] = static_cast<__nv_bfloat16*>(a->ring_hi[l]);
+    p.ring_lo[l] = static_cast<__nv_bfloat16*>(a->ring_lo[l]);
+  }
+  if ((rc = encode_tmap_bf16_planes(&p.tm_c, a->cond_hi, a->cond_lo, a->n_mels, W, B * a->n_group, a->n_mels, W * a->n_mels, 128)))
+    return rc;
+  p.batch = a->batch; p.w = a->width; p.n_layers = a->n_layers; p.n_group = a->n_group; p.n_rows = a->n_group - 1;
+  p.tiles_per_b = (a->width + 255) / 256;
+  p.tiles_per_step = p.tiles_per_b * a->batch;
+  const long long total = static_cast<long long>(p.tiles_per_step) * p.n_rows * p.n_layers;
+  PK_CHECK_ARG(total < (1ll << 30) && a->flags_len >= total, "flags must hold one counter per tile (%lld)", total);
+  p.total_tiles = static_cast<int>(total);
+  p.cond_ksteps_last = (a->n_mels - 64 + kUmmaK - 1) / kUmmaK;
+  for (int i = 0; i < a->n_group; ++i) {
+    PK_CHECK_ARG(a->cond_rows[i] >= 0 && a->cond_rows[i] < a->n_group, "cond_rows[%d] out of range", i);
+    p.cmap[i] = a->cond_rows[i];
+  }
+  for (int i = 0; i < kCh; ++i) { p.in_w[i] = a->in_w[i]; p.in_b[i] = a->in_b[i]; p.po_w[i] = a->out_w[i]; p.po_w[kCh + i] = a->out_w[kCh + i]; }
+  p.po_b[0] = a->out_b[0]; p.po_b[1] = a->out_b[1];
+  p.k_a = -2.f * kLog2e; p.k_g = -kLog2e;
+  p.skip = a->skip; p.z = a->z; p.x = a->x; p.flags = a->flags;
+  // a pair finishes a tile before it starts the next one: a tile may wait for the pair's own previous tile, any grid size works
+  const int n_pairs = std::max(1, std::min(max_pairs, p.tiles_per_step));
+  waveflow_flow128_kernel<<<2 * n_pairs, kThreads, kSmem128, static_cast<cudaStream_t>(stream)>>>(p);
+  PK_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return PK_OK;
+}
+
 extern "C" int pk_waveflow_flow(const pk_waveflow_flow_args* a, pk_stream_t stream) {
   using namespace pk;
   using namespace pk::wf;
   PK_CHECK_ARG(a != nullptr, "args is NULL");
   PK_CHECK_ARG(a->batch > 0 && a->width > 0, "bad batch/width");
-  PK_CHECK_ARG(a->channels == kC, "the fused WaveFlow flow is built for 64 residual channels (got %d)", a->channels);
+  PK_CHECK_ARG(a->channels == kC || a->channels == c128::kCh, "the fused WaveFlow flow is built for 64 or 128 residual channels (got %d)",
+               a->channels);
   PK_CHECK_ARG(a->n_mels > 64 && a->n_mels <= 128 && (a->n_mels % 8) == 0, "n_mels must be in (64, 128], a multiple of 8");
   PK_CHECK_ARG(a->n_layers >= 1 && a->n_layers <= kMaxLayers && a->n_group >= 2 && a->n_group <= kMaxGroup,
                "n_layers must be 1..8 (width dilation 2^l <= 128) and n_group 2..16");
   PK_CHECK_ARG(a->cond_rows && a->ring_hi && a->ring_lo && a->cond_hi && a->cond_lo && a->w1_hi && a->w1_lo && a->w2_hi && a->w2_lo &&
                a->bias1 && a->bias2 && a->in_w && a->in_b && a->out_w && a->out_b && a->z && a->x && a->skip && a->flags,
                "NULL pointer in pk_waveflow_flow_args");
+  if (a->channels == c128::kCh) return flow128_launch(a, stream);
   static int max_pairs = 0;
   static bool attr_set = false;
   if (!attr_set) {

@@ -111,22 +111,27 @@ class ConditionalWaveFlow(Layer):
                         wk[:, s * C:(s + 1) * C, :] = w[:, :, (s - v) % 3, :]
                     variants.append(ops.pack_weight(wk, dev))
                 fused = None
-                if self._fusable():
-                    # operands of pk_waveflow_layer (include/parakeet_b200.h): GEMM1 weight per row-step variant =
-                    # [tap][slot][c] conv columns | condition_proj columns, both planes in one allocation; out_proj as skip | res
+                if self._eligible():
+                    # operands of pk_waveflow_flow / pk_waveflow_layer (include/parakeet_b200.h): channels in blocks of 64; gate rows
+                    # a_blk | g_blk per block, out_proj rows skip_blk | res_blk; GEMM1 columns [tap][slot][c] | condition_proj
+                    nb = C // 64
+                    g_rows = torch.cat([torch.cat([torch.arange(64 * k, 64 * k + 64), torch.arange(C + 64 * k, C + 64 * k + 64)])
+                                        for k in range(nb)])
+                    o_rows = torch.cat([torch.cat([torch.arange(C + 64 * k, C + 64 * k + 64), torch.arange(64 * k, 64 * k + 64)])
+                                        for k in range(nb)])
                     cw = p[q + "condition_proj.weight"][:, :, 0, 0]
                     w1 = []
                     for v in range(3):
-                        m = torch.zeros(2 * C, 11 * 64)
+                        m = torch.zeros(2 * C, 9 * C + 128)
                         for tap in range(3):
                             for s in range(3):
-                                m[:, 192 * tap + 64 * s:192 * tap + 64 * s + 64] = w[:, :, (s - v) % 3, tap]
-                        m[:, 576:576 + self.n_mels] = cw
-                        w1.append(_planes(m, dev))
+                                m[:, (3 * tap + s) * C:(3 * tap + s + 1) * C] = w[:, :, (s - v) % 3, tap]
+                        m[:, 9 * C:9 * C + self.n_mels] = cw
+                        w1.append(_planes(m[g_rows], dev))
                     ow, ob = p[q + "out_proj.weight"][:, :, 0, 0], p[q + "out_proj.bias"]
-                    fused = dict(w1=w1, w2=_planes(torch.cat([ow[C:], ow[:C]], dim=0), dev),
-                                 b1=(p[q + "conv.bias"] + p[q + "condition_proj.bias"]).numpy().astype("float32").copy(),
-                                 b2=torch.cat([ob[C:], ob[:C]]).numpy().astype("float32").copy())
+                    fused = dict(w1=w1, w2=_planes(ow[o_rows], dev),
+                                 b1=(p[q + "conv.bias"] + p[q + "condition_proj.bias"])[g_rows].numpy().astype("float32").copy(),
+                                 b2=ob[o_rows].numpy().astype("float32").copy())
                 layers.append(dict(fused=fused, conv=variants, conv_b=p[q + "conv.bias"].to(dev),
                                    cond=ops.pack_weight(p[q + "condition_proj.weight"][:, :, 0, 0], dev),
                                    cond_b=p[q + "condition_proj.bias"].to(dev),
@@ -147,14 +152,17 @@ class ConditionalWaveFlow(Layer):
         return pk
 
     def _fusable(self):
-        """The fused kernels (pk_waveflow_flow: one persistent launch per flow; pk_waveflow_layer: one launch per
-        ResidualBlock.add_input) cover 64 residual channels and 64 < n_mels <= 128.  PK_WF_FUSED=layer selects the per-layer
-        kernel, PK_WF_FUSED=0 the two-GEMM path (A/B runs)."""
-        return (self.channels == 64 and 64 < self.n_mels <= 128 and self.n_mels % 8 == 0
-                and os.environ.get("PK_WF_FUSED", "1") != "0")
+        """The fused kernels cover 64 < n_mels <= 128 and up to 8 layers per flow: pk_waveflow_flow (one persistent launch per
+        flow) for 64 or 128 residual channels, pk_waveflow_layer (one launch per ResidualBlock.add_input, PK_WF_FUSED=layer)
+        for 64.  PK_WF_FUSED=0 selects the two-GEMM path (A/B runs; also what other channel counts use)."""
+        mode = os.environ.get("PK_WF_FUSED", "1")
+        return self._eligible() and mode != "0" and (mode != "layer" or self.channels == 64)
+
+    def _eligible(self):
+        return self.channels in (64, 128) and 64 < self.n_mels <= 128 and self.n_mels % 8 == 0 and self.n_layers <= 8
 
     def _flow_mode(self):
-        return self._fusable() and self.n_layers <= 8 and os.environ.get("PK_WF_FUSED", "1") != "layer"
+        return self._fusable() and os.environ.get("PK_WF_FUSED", "1") != "layer"
 
     def _run_flow(self, fw, z, x, cond_s, cmap, bufs, skip, flags, prof, st):
         """Rows 1 .. G-1 of one flow in one launch (row 0 and the ring contents are prepared by the caller)."""
