@@ -507,6 +507,21 @@ def main():
             wf_ms = e0.elapsed_time(e1) / 3
             out["extra"]["waveflow_b16_c64"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
                                                 "note": "cfg4; one persistent dataflow launch per flow (pk_waveflow_flow), one CUDA graph per call"}
+            # the same batch on the reference's shipped WaveFlow config (examples/waveflow/config.py: 128 residual channels)
+            del wf
+            wf2 = ConditionalWaveFlow([16, 16], 8, 8, 16, 128, 80, (3, 3), device=dev, seed=5)
+            for _ in range(3):
+                wf2.infer(melw, z=zw)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                aw = wf2.infer(melw, z=zw)
+            e1.record()
+            torch.cuda.synchronize()
+            wf_ms = e0.elapsed_time(e1) / 3
+            out["extra"]["waveflow_b16_c128"] = {"samples_per_s": aw.numel() / (wf_ms * 1e-3), "ms_per_step": wf_ms,
+                                                 "note": "shipped config (128 channels), same batch as cfg4"}
+            del wf2
             # Parallel WaveGAN training step (the workload of the reference's own benchmark harness, tests/benchmark/PWGAN/
             # run_benchmark.sh: batch 6, batch_max_steps 25 500, metric sequences/s), past discriminator_train_start_steps: generator
             # step with the adversarial term + discriminator step

@@ -264,33 +264,42 @@ def test_waveflow_layer_paths_agree(cuda, monkeypatch, mode):
     assert rel_err(m2.infer(mel.to(cuda), z=z.to(cuda)), out) < 1e-4
 
 
-def test_waveflow_shipped_config_128_channels(cuda):
-    """examples/waveflow/config.py ships channels = 128 (BASELINE cfg 4 is the 64-channel variant): N = 256 gate channels,
-    K = 3 x 384 per tap through pk_conv_gemm_ex (the fused kernels cover 64 channels)."""
+def test_waveflow_shipped_config_128_channels(cuda, monkeypatch):
+    """examples/waveflow/config.py ships channels = 128 (BASELINE cfg 4 is the 64-channel variant): the flow kernel runs the
+    channels as two blocks of 64 (N = 256 MMAs); W = 431 columns so that every width dilation reaches live columns; the
+    two-GEMM path (PK_WF_FUSED=0: N = 256 gate channels, K = 3 x 384 per tap through pk_conv_gemm_ex) must agree."""
     from oracle import waveflow as owf
     from parakeet_b200.models import ConditionalWaveFlow
     params = owf.synth_params(5, channels=128)
     folded = owf.fold_weight_norm(params)
-    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 128, 80, (3, 3), device=cuda)
-    m.set_state_dict(params)
     g = torch.Generator().manual_seed(55)
-    mel = torch.randn(2, 80, 20, generator=g) * 0.5 - 3
-    z = torch.randn(2, 256 * 20 - 272, generator=g)
+    mel = torch.randn(3, 80, 28, generator=g) * 0.5 - 3
+    z = torch.randn(3, 256 * 28 - 272, generator=g)
     with torch.no_grad():
         ref = owf.infer(folded, mel, z)
-    out = m.infer(mel.to(cuda), z=z.to(cuda))
-    assert list(out.shape) == list(ref.shape) and rel_err(out, ref) < TOL
+    outs = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PK_WF_FUSED", mode)
+        m = ConditionalWaveFlow([16, 16], 8, 8, 16, 128, 80, (3, 3), device=cuda)
+        m.set_state_dict(params)
+        assert m._flow_mode() == (mode == "1")
+        out = m.infer(mel.to(cuda), z=z.to(cuda))
+        assert list(out.shape) == list(ref.shape) and rel_err(out, ref) < TOL, mode
+        outs.append(out)
+    assert rel_err(outs[0], outs[1]) < 1e-4
 
 
-def test_waveflow_flow_kernel_single_utterance_and_edges(cuda):
+@pytest.mark.parametrize("channels", [64, 128])
+def test_waveflow_flow_kernel_single_utterance_and_edges(cuda, channels):
     """pk_waveflow_flow scheduling corners: one utterance with a single tile per step (every tile depends on the pair's own
-    previous tile: unpipelined issue order), two tiles per step, and a width just past a tile boundary (257 columns)."""
+    previous tile: unpipelined issue order), two tiles per step, and a width just past a tile boundary (271 columns)."""
     from oracle import waveflow as owf
     from parakeet_b200.models import ConditionalWaveFlow
-    params = owf.synth_params(4)
+    params = owf.synth_params(4, channels=channels)
     folded = owf.fold_weight_norm(params)
-    m = ConditionalWaveFlow([16, 16], 8, 8, 16, 64, 80, (3, 3), device=cuda)
+    m = ConditionalWaveFlow([16, 16], 8, 8, 16, channels, 80, (3, 3), device=cuda)
     m.set_state_dict(params)
+    assert m._flow_mode()
     for batch, frames, seed in ((1, 9, 51), (1, 18, 52), (2, 18, 53)):     # W = 127, 271, 271
         g = torch.Generator().manual_seed(seed)
         mel = torch.randn(batch, 80, frames, generator=g) * 0.5 - 3
