@@ -909,8 +909,8 @@ waveflow_flow128_kernel(const __grid_constant__ Flow128Args p) {
   const uint32_t acc1_full = empty_bar + 8 * kStages3;
   const uint32_t acc2_full = acc1_full + 8;
   const uint32_t acc2_empty = acc2_full + 8;                   // leader
-  const uint32_t z_full = acc2_empty + 8;                      // leader
-  const uint32_t tmem_slot = z_full + 8;
+  const uint32_t z_full = acc2_empty + 8;                      // [2] leader: z of channel block 0 / 1 is in tensor memory
+  const uint32_t tmem_slot = z_full + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -924,6 +924,7 @@ waveflow_flow128_kernel(const __grid_constant__ Flow128Args p) {
     mbar_init_a(acc2_full, 1);
     mbar_init_a(acc2_empty, 2 * kStoreWarps);
     mbar_init_a(z_full, 2 * kGateWarps);
+    mbar_init_a(z_full + 8, 2 * kGateWarps);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm_a<512>(tmem_slot);
@@ -1036,10 +1037,9 @@ waveflow_flow128_kernel(const __grid_constant__ Flow128Args p) {
           umma_commit_2sm_a(empty_bar + 8 * s);
         }
         umma_commit_2sm_a(acc1_full);
-        mbar_wait_a(z_full, i & 1);                  // z of both blocks is in tensor memory (over the a-columns of acc1)
-        tcgen05_fence_after();
         for (int kc = 0; kc < kG2Chunks; ++kc, ++it) {
           const int s = it % kStages3;
+          mbar_wait_a(z_full + 8 * kc, i & 1);       // z of block kc is in tensor memory (over the a-columns of acc1): K-chunk kc of GEMM2
           mbar_wait_a(full_bar + 8 * s, (it / kStages3) & 1);
           tcgen05_fence_after();
           const uint32_t st = smem + s * kStage;
@@ -1098,11 +1098,11 @@ waveflow_flow128_kernel(const __grid_constant__ Flow128Args p) {
           }
           tmem_st_32x32(acc + half * 32, zw);
         }
+        tmem_st_wait();                  // block blk is complete: GEMM2 can start on it while the other block is gated
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed_a(z_full_l + 8 * blk);
       }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed_a(z_full_l);
     }
   } else {
     // ------------------------------ store warps ------------------------------
