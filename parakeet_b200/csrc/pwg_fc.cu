@@ -114,16 +114,21 @@ struct FcTileIter {   // 256-sample tiles of the pair; this CTA owns rows [m0 + 
   }
 };
 
-// kResidMma: the residual add `+ x` as a tensor-core pass (x [0 | I] into the GEMM2 accumulator, 8 MMAs per tile, no global
+// kResid selects where the residual add `+ x` happens.  2 (PK_PWG_RESID=gate): the gate warps preload the GEMM2 accumulator
+// with [0 | x_hi + x_lo] (x re-read from global memory - L2 hot, TMA has just streamed it - and written with tcgen05.st while
+// GEMM1 of the tile is still running), GEMM2 accumulates on top: no extra MMAs and nothing added to the store warps.
+// 1 (kResidMma): the residual add `+ x` as a tensor-core pass (x [0 | I] into the GEMM2 accumulator, 8 MMAs per tile, no global
 // loads) or, when false, in the out-store warps from global memory (the rows were just streamed by TMA, so they hit L2):
 // 8 fewer shared-memory-fed MMAs against 16 LDG.128 per thread and tile.  PK_PWG_RESID=ldg selects the latter (experiment).
-template <bool kProf, bool kResidMma>
+template <bool kProf, int kResid>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwgThreads, 1)
 pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_u,
                     const __grid_constant__ CUtensorMap tm_p,          // 4-D maps: both planes of a tile in one TMA box
                       const __grid_constant__ CUtensorMap tm_w1_hi, const __grid_constant__ CUtensorMap tm_w1_lo,
                       const __grid_constant__ CUtensorMap tm_w2_hi, const __grid_constant__ CUtensorMap tm_w2_lo,
                       const FcLayerArgs p) {
+  constexpr bool kResidMma = kResid == 1;
+  constexpr bool kResidGate = kResid == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w1 = smem + kFcStages * kFcStageBytes;        // [chunk][hi | lo] 64-row tiles, resident
@@ -153,7 +158,8 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     for (int s = 0; s < kFcStages; ++s) { mbar_init_a(full_bar + 8 * s, 1); mbar_init_a(empty_bar + 8 * s, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init_a(acc1_full + 8 * i, 1);
-      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, 2 * kPwgStoreWarps);
+      // kResidGate: each CTA's gate warps wait for their own CTA's store warps (local barrier); else the issuer waits for both CTAs'
+      mbar_init_a(acc2_full + 8 * i, 1); mbar_init_a(acc2_empty + 8 * i, kResidGate ? kPwgStoreWarps : 2 * kPwgStoreWarps);
       mbar_init_a(z_full + 8 * i, 2 * kPwgGateWarps);
     }
     mbar_init_a(w_bar, 1);
@@ -303,7 +309,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         PK_TICK(2)
         mbar_wait_a(z_full + 8 * buf, (i >> 1) & 1);   // the gate warps of both CTAs wrote z over acc1(buf), tcgen05.wait::st done
         PK_TICK(3)
-        if (!kResidMma) {
+        if (kResid == 0) {
           mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);
           PK_TICK(4)
         }
@@ -316,7 +322,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
         for (int k = 0; k < 4; ++k) {
           const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
           const uint32_t a_hi = za + 32 * (k >> 1) + 8 * (k & 1), a_lo = a_hi + 16;
-          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, kResidMma || k != 0);   // on top of the residual pass (if any)
+          umma_bf16_2sm_ts(d2, a_hi, b_hi + koff, idesc, kResid != 0 || k != 0);   // on top of the residual pass / preload (if any)
           umma_bf16_2sm_ts(d2, a_lo, b_hi + koff, idesc, 1);
           umma_bf16_2sm_ts(d2, a_hi, b_lo + koff, idesc, 1);
         }
@@ -356,6 +362,39 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     for (int i = 0; ti.next(b, m0); ++i) {
       const int buf = i & 1;
       PK_TICK(6)
+      if (kResidGate) {
+        // GEMM2's accumulator starts as [0 | x]: this thread's row, 64 channels, while GEMM1 of the tile is still in flight
+        const int trow = m0 + 128 * static_cast<int>(rank) + r;
+        const bool in = trow < p.t;
+        const long long row_off = (static_cast<long long>(b) * p.t + trow) * 64;
+        uint4 xh[8], xl[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          xh[q] = in ? __ldg(reinterpret_cast<const uint4*>(p.x_hi + row_off) + q) : make_uint4(0, 0, 0, 0);
+          xl[q] = in ? __ldg(reinterpret_cast<const uint4*>(p.x_lo + row_off) + q) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait_a(acc2_empty + 8 * buf, ((i >> 1) & 1) ^ 1);     // this CTA's store warps have read tile i-2
+        tcgen05_fence_after();
+        const uint32_t acc2 = tmem_base + lane_base + 256 + buf * 128;
+        uint32_t f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = 0u;
+        __syncwarp();
+        tmem_st_32x32(acc2, f);
+        tmem_st_32x32(acc2 + 32, f);
+        const uint32_t* wh = reinterpret_cast<const uint32_t*>(xh);
+        const uint32_t* wl = reinterpret_cast<const uint32_t*>(xl);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            f[2 * e] = __float_as_uint(__uint_as_float(wh[16 * h + e] << 16) + __uint_as_float(wl[16 * h + e] << 16));
+            f[2 * e + 1] = __float_as_uint(__uint_as_float(wh[16 * h + e] & 0xffff0000u) + __uint_as_float(wl[16 * h + e] & 0xffff0000u));
+          }
+          tmem_st_32x32(acc2 + 64 + 32 * h, f);
+        }
+        // (tcgen05.wait::st before the z_full arrive below covers these stores)
+      }
       mbar_wait_a(acc1_full + 8 * buf, (i >> 1) & 1);
       PK_TICK(0)
       tcgen05_fence_after();
@@ -399,7 +438,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const int quarter = warp & 3;
     const int half = sw >> 2;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t acc2_empty_l = mapa_shared(acc2_empty, 0);
+    const uint32_t acc2_empty_l = mapa_shared(acc2_empty, kResidGate ? rank : 0);
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
     FcTileIter ti(p);
@@ -459,7 +498,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             xl[q] = live ? __ldg(reinterpret_cast<const uint4*>(p.x_lo + row_off + pass * 32) + q) : make_uint4(0, 0, 0, 0);
           }
         };
-        if (!kResidMma) load_x(0);                // issued before the wait: the latency hides behind GEMM2 of this tile
+        if (kResid == 0) load_x(0);               // issued before the wait: the latency hides behind GEMM2 of this tile
         PK_TICK(6)
         mbar_wait_a(acc2_full + 8 * buf, (i >> 1) & 1);
         PK_TICK(0)
@@ -476,7 +515,7 @@ pwg_layer_fc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed_a(acc2_empty_l + 8 * buf);
           }
-          if (!kResidMma) {
+          if (kResid == 0) {
             const uint32_t* wh = reinterpret_cast<const uint32_t*>(xh);
             const uint32_t* wl = reinterpret_cast<const uint32_t*>(xl);
 #pragma unroll
@@ -550,10 +589,12 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   if ((rc = encode_tmap_bf16_3d(&tw2_lo, a->w2_lo, 64, 128, 1, 64, 0, 64))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
-    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+    PK_CHECK_CUDA(cudaFuncSetAttribute(pwg_layer_fc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
     attr_set = true;
   }
   FcLayerArgs p;
@@ -574,12 +615,15 @@ extern "C" int pk_pwg_residual_layer_fc(const pk_pwg_layer_fc_args* a, pk_stream
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int pair_tiles = ((a->t + 255) / 256) * a->batch;
   const int grid = 2 * std::min(pair_tiles, sm_count() / 2);
-  static const bool resid_mma = [] { const char* e = getenv("PK_PWG_RESID"); return !(e && strcmp(e, "ldg") == 0); }();
+  static const int resid = [] {
+    const char* e = getenv("PK_PWG_RESID");
+    return e && strcmp(e, "ldg") == 0 ? 0 : e && strcmp(e, "gate") == 0 ? 2 : 1;
+  }();
 #define PK_FC_LAUNCH(PROF, RES) pwg_layer_fc_kernel<PROF, RES><<<grid, kPwgThreads, kFcSmem, st>>>(tx, tu, tp, tw1_hi, tw1_lo, tw2_hi, tw2_lo, p)
   if (p.prof != nullptr) {
-    if (resid_mma) PK_FC_LAUNCH(true, true); else PK_FC_LAUNCH(true, false);
+    if (resid == 0) PK_FC_LAUNCH(true, 0); else if (resid == 1) PK_FC_LAUNCH(true, 1); else PK_FC_LAUNCH(true, 2);
   } else {
-    if (resid_mma) PK_FC_LAUNCH(false, true); else PK_FC_LAUNCH(false, false);
+    if (resid == 0) PK_FC_LAUNCH(false, 0); else if (resid == 1) PK_FC_LAUNCH(false, 1); else PK_FC_LAUNCH(false, 2);
   }
 #undef PK_FC_LAUNCH
   PK_CHECK_CUDA(cudaGetLastError());

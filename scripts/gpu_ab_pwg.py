@@ -28,6 +28,10 @@ for rep in range(3):
     best = min(best, e0.elapsed_time(e1) / 8)
 print("%%-40s err %%.2e  %%.2f ms per batch" %% (os.environ.get("TAG"), err, best), flush=True)
 ''' % ROOT
-for tag, env in (("resid=mma (default)", {}), ("resid=ldg", {"PK_PWG_RESID": "ldg"}), ("resid=mma again", {}), ("round-1 kernel", {"PK_PWG_FRAME_COND": "0"})):
+VARIANTS = (("resid=mma", {"PK_PWG_RESID": "mma"}), ("resid=gate", {"PK_PWG_RESID": "gate"}), ("resid=ldg", {"PK_PWG_RESID": "ldg"}),
+            ("resid=mma again", {"PK_PWG_RESID": "mma"}), ("resid=gate again", {"PK_PWG_RESID": "gate"}))
+if "--all" in sys.argv:
+    VARIANTS += (("round-1 kernel", {"PK_PWG_FRAME_COND": "0"}),)
+for tag, env in VARIANTS:
     e = dict(os.environ, TAG=tag, **env)
     subprocess.run([sys.executable, "-c", CODE], env=e)
