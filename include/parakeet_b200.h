@@ -440,6 +440,9 @@ int pk_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, int64_t 
                    void* ds_hi, void* ds_lo, pk_stream_t stream);
 /* out[c] += sum_rows x[row, c] (bias gradients). */
 int pk_colsum(const float* x, int64_t rows, int32_t c, float* out, pk_stream_t stream);
+/* out[i] = sum_{s < slices} part[s * n + i] (fp32): the reduction of split-K partial products of a weight gradient; overwrites
+ * `out` (unlike pk_colsum, which accumulates). */
+int pk_sum_slices(const float* part, int32_t slices, int64_t n, float* out, pk_stream_t stream);
 /* BatchNorm1D in training mode on (rows, c) (tacotron2/decoder.py:128-180 under model.train()): batch statistics
  * (biased variance), y = act(gamma * xhat + beta) with act in {PK_ACT_NONE, PK_ACT_TANH}, running statistics updated with
  * Paddle's momentum (running = momentum * running + (1 - momentum) * batch); saves mean / rstd for the backward. */

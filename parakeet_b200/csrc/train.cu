@@ -156,6 +156,27 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   if (ty == 0 && col < c) atomicAdd(out + col, part[0][tx] + part[1][tx] + part[2][tx] + part[3][tx]);
 }
 
+// out[i] = sum_s part[s][i]: the reduction of split-K partial products (overwrites: no zero fill, no copy afterwards)
+__global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, int s, long long n, float* __restrict__ out,
+                                                         int vec) {
+  const long long i = (blockIdx.x * 256LL + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (vec) {                     // n % 4 == 0 and both pointers 16-byte aligned
+    float4 a = *reinterpret_cast<const float4*>(part + i);
+    for (int k = 1; k < s; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(part + k * n + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = a;
+  } else {
+    for (long long j = i; j < n && j < i + 4; ++j) {
+      float a = part[j];
+      for (int k = 1; k < s; ++k) a += part[k * n + j];
+      out[j] = a;
+    }
+  }
+}
+
 // per-column sum and sum of squares (BatchNorm batch statistics): sums[c] += sum x, sums[C + c] += sum x^2
 __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ x, long long rows, int c, float* __restrict__ sums) {
   __shared__ float p1[4][64], p2[4][64];
@@ -446,6 +467,13 @@ extern "C" int pk_colsum(const float* x, int64_t rows, int32_t c, float* out, pk
   PK_CHECK_ARG(x && out && rows > 0 && c > 0, "bad arguments");
   dim3 grid(static_cast<unsigned>((rows + 63) / 64), (c + 63) / 64);
   colsum_kernel<<<grid, 256, 0, PK_STREAM>>>(x, rows, c, out);
+  PK_LAUNCH_DONE()
+}
+
+extern "C" int pk_sum_slices(const float* part, int32_t slices, int64_t n, float* out, pk_stream_t stream) {
+  PK_CHECK_ARG(part && out && slices > 0 && n > 0, "bad arguments");
+  const int vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  sum_slices_kernel<<<nblk((n + 3) / 4, 256), 256, 0, PK_STREAM>>>(part, slices, n, out, vec);
   PK_LAUNCH_DONE()
 }
 

@@ -341,6 +341,14 @@ def colsum_(x, out):
     _lib.check(_lib.lib().pk_colsum(_ptr(x), x.numel() // c, c, _ptr(out), _stream()), "pk_colsum")
 
 
+def sum_slices(part, out):
+    """out = part.sum(0) for fp32 part (S, ...) and contiguous out (split-K reduction; overwrites out)."""
+    s = part.shape[0]
+    assert part.is_contiguous() and out.is_contiguous() and part.numel() == s * out.numel()
+    _lib.check(_lib.lib().pk_sum_slices(_ptr(part), s, out.numel(), _ptr(out), _stream()), "pk_sum_slices")
+    return out
+
+
 def relu_bwd(dy, y_split, want_f32=False):
     dx = torch.empty_like(dy) if want_f32 else None
     dxs = Split.empty(tuple(dy.shape), dy.device)

@@ -165,12 +165,12 @@ def _wgrad_splitk(dys, x, cout, cin, k, shifts):
     dev = dys.hi.device
     cout_p, cin_p = dys.hi.shape[-1], x.hi.shape[-1]
     Tp, S, ks, KKp = wgrad.plan(B, T, cout_p, cin_p)
-    dyt = Split.zeros((cout_p, KKp), dev)
+    dyt = wgrad.zero_planes(("dyt", B, T), (cout_p, KKp), dev)
     ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout_p, ld_src=cout_p, c0=0, cols=cout_p, shift=0, r_out=T, dst=dyt,
                          dst_zstride=Tp, ld_dst=KKp)
     out = torch.empty(len(shifts), cout_p, cin_p, dtype=torch.float32, device=dev)
     for j, sh in enumerate(shifts):
-        xt = Split.zeros((cin_p, KKp), dev)
+        xt = wgrad.zero_planes(("xt", B, T), (cin_p, KKp), dev)
         ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin_p, shift=sh, r_out=T, dst=xt,
                              dst_zstride=Tp, ld_dst=KKp)
         wgrad.nt_splitk(dyt, xt, cout_p, cin_p, S, ks, KKp, out=out[j])

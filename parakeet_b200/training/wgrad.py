@@ -1,10 +1,24 @@
 """Split-K weight gradients: dW = A^T-style NT matmuls whose reduction axis is the flattened (batch, time) axis (10^4 .. 10^6)
 while the output is a handful of 128 x N tiles.  K is cut into S slices so that tiles x S fills the machine: S independent NT
-matmuls (`pk_conv_gemm` batched over the slices) whose fp32 partial results are summed by `pk_colsum`."""
+matmuls (`pk_conv_gemm` batched over the slices) whose fp32 partial results are summed by `pk_sum_slices`."""
 import torch
 
 from .. import ops
 from ..ops import Split
+
+
+_ZERO_PLANES = {}
+
+
+def zero_planes(role, shape, dev):
+    """Persistent zero-initialised split planes for a transposed GEMM operand.  `transpose_planes` rewrites the same valid region
+    on every use of a (role, shape) key and never touches the K padding, so the zeros are written once, not by a fill kernel per
+    use.  `role` carries whatever fixes the valid region (batch, time, ...) and keeps operands that are alive together apart."""
+    key = (role, tuple(shape), str(dev))
+    buf = _ZERO_PLANES.get(key)
+    if buf is None:
+        buf = _ZERO_PLANES[key] = Split.zeros(tuple(shape), dev)
+    return buf
 
 
 def plan(batch, t, m, n, max_slices=128):
@@ -29,10 +43,9 @@ def nt_splitk(at, bt, m, n, s, ks, kkp, out=None):
     part = torch.empty(s, m, n, dtype=torch.float32, device=dev)
     ops.batched_matmul_nt(at, bt, batch=s, heads=1, m=m, n=n, k=ks, a_spec=sa, b_spec=sb, y_f32=part, y_batch_stride=m * n, y_head_stride=0,
                           y_ld=n)
-    y = torch.zeros(m * n, dtype=torch.float32, device=dev)
-    ops.colsum_(part.reshape(s, m * n), y)
-    y = y.reshape(m, n)
-    if out is not None:
+    y = out if (out is not None and out.is_contiguous()) else torch.empty(m, n, dtype=torch.float32, device=dev)
+    ops.sum_slices(part, y)
+    if out is not None and y is not out:
         out.copy_(y)
         return out
     return y
