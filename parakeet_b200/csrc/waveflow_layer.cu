@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "pk_host.h"
 #include "pk_sm100.cuh"
@@ -1282,6 +1283,8 @@ static int flow128_launch(const pk_waveflow_flow_args* a, pk_stream_t stream) {
   using namespace pk::wf;
   using namespace pk::wf::c128;
   PK_CHECK_ARG(a->prof == nullptr, "no phase counters in the 128-channel flow kernel");
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   static int max_pairs = 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1301,7 +1304,7 @@ static int flow128_launch(const pk_waveflow_flow_args* a, pk_stream_t stream) {
     max_pairs = std::min(n, sm_count() / 2);
     attr_set = true;
   }
-  static Flow128Args p;
+  static Flow128Args p;   // built in place under `mu`; the launch copies it
   const uint64_t W = a->width, B = a->batch;
   int rc;
   constexpr float kLog2e = 1.4426950408889634f;
@@ -1363,6 +1366,8 @@ extern "C" int pk_waveflow_flow(const pk_waveflow_flow_args* a, pk_stream_t stre
                a->bias1 && a->bias2 && a->in_w && a->in_b && a->out_w && a->out_b && a->z && a->x && a->skip && a->flags,
                "NULL pointer in pk_waveflow_flow_args");
   if (a->channels == c128::kCh) return flow128_launch(a, stream);
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   static int max_pairs = 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1384,7 +1389,7 @@ extern "C" int pk_waveflow_flow(const pk_waveflow_flow_args* a, pk_stream_t stre
     max_pairs = std::min(n, sm_count() / 2);
     attr_set = true;
   }
-  static FlowArgs p;       // 14 KB of kernel parameters: built in place (host calls are serialised by the Python layer)
+  static FlowArgs p;       // 14 KB of kernel parameters, built in place under `mu`; the launch copies them
   const uint64_t W = a->width, B = a->batch;
   int rc;
   for (int l = 0; l < a->n_layers; ++l) {
