@@ -164,3 +164,37 @@ def test_fused_attention_vs_fp64(cuda):
         err = (ctx - ref).abs().max().item() / ref.abs().max().item()
         assert err < 2e-5, (B, T, H, dk, err)
         assert ctx[~keep].abs().max().item() == 0 if lens else True
+
+
+def test_sum_slices_and_splitk_wgrad(cuda):
+    """pk_sum_slices (split-K reduction, overwrites its output): the float4 path, the scalar path (n % 4 != 0 or a misaligned
+    view of the flat gradient buffer), and wgrad.nt_splitk writing into a non-contiguous destination; the persistent zero
+    planes of the transposed operands give the same gradient on a second use with other data."""
+    from parakeet_b200 import ops
+    from parakeet_b200.training import wgrad
+    g = torch.Generator().manual_seed(21)
+    for s, n, off in ((7, 4096, 0), (128, 384 * 3, 0), (5, 1001, 0), (3, 64, 1)):
+        part = torch.randn(s, n, generator=g).to(cuda)
+        flat = torch.full((n + 8,), 7.0, device=cuda)            # garbage the call must overwrite
+        out = flat[off:off + n]
+        ops.sum_slices(part, out)
+        ref = part.double().sum(0)
+        assert (out.double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+        assert flat[off + n:].eq(7.0).all() and flat[:off].eq(7.0).all()
+    # dW = X^T dY over (batch, time), with the padded / persistent operand planes used twice
+    B, T, cin, cout = 3, 150, 96, 200
+    for rep in range(2):
+        x = torch.randn(B, T, cin, generator=g).to(cuda)
+        dy = torch.randn(B, T, cout, generator=g).to(cuda)
+        Tp, S, ks, KKp = wgrad.plan(B, T, cin, cout)
+        xs, dys = ops.Split.from_f32(x), ops.Split.from_f32(dy)
+        xt = wgrad.zero_planes(("test_xt", B, T), (cin, KKp), cuda)
+        dyt = wgrad.zero_planes(("test_dyt", B, T), (cout, KKp), cuda)
+        ops.transpose_planes(xs, z=B, rows=T, src_zstride=T * cin, ld_src=cin, c0=0, cols=cin, shift=0, r_out=T, dst=xt, dst_zstride=Tp, ld_dst=KKp)
+        ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout, ld_src=cout, c0=0, cols=cout, shift=0, r_out=T, dst=dyt, dst_zstride=Tp,
+                             ld_dst=KKp)
+        big = torch.zeros(cin, cout + 8, device=cuda)
+        out = big[:, :cout] if rep else torch.empty(cin, cout, device=cuda)      # second pass: non-contiguous destination
+        got = wgrad.nt_splitk(xt, dyt, cin, cout, S, ks, KKp, out=out)
+        ref = torch.einsum("btc,btd->cd", xs.float().double().cpu(), dys.float().double().cpu())
+        assert (got.double().cpu() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
