@@ -36,14 +36,18 @@ def nt_splitk(at, bt, m, n, s, ks, kkp, out=None):
     dev = at.hi.device
     sa = dict(rows=m, cols=ks, ld=kkp, batch_stride=ks, batches=s, bmul=1, hmul=0, col0=0, colh=0)
     sb = dict(rows=n, cols=ks, ld=kkp, batch_stride=ks, batches=s, bmul=1, hmul=0, col0=0, colh=0)
+    direct = out is not None and out.is_contiguous()
     if s == 1:
-        y = out if out is not None else torch.empty(m, n, dtype=torch.float32, device=dev)
+        y = out if direct else torch.empty(m, n, dtype=torch.float32, device=dev)
         ops.batched_matmul_nt(at, bt, batch=1, heads=1, m=m, n=n, k=ks, a_spec=sa, b_spec=sb, y_f32=y, y_batch_stride=0, y_head_stride=0, y_ld=n)
+        if out is not None and not direct:
+            out.copy_(y)
+            return out
         return y
     part = torch.empty(s, m, n, dtype=torch.float32, device=dev)
     ops.batched_matmul_nt(at, bt, batch=s, heads=1, m=m, n=n, k=ks, a_spec=sa, b_spec=sb, y_f32=part, y_batch_stride=m * n, y_head_stride=0,
                           y_ld=n)
-    y = out if (out is not None and out.is_contiguous()) else torch.empty(m, n, dtype=torch.float32, device=dev)
+    y = out if direct else torch.empty(m, n, dtype=torch.float32, device=dev)
     ops.sum_slices(part, y)
     if out is not None and y is not out:
         out.copy_(y)
