@@ -2,6 +2,7 @@
 energy (data/get_feats.py:205-220), checkpoint writer round trip, ConditionalWaveFlow.from_pretrained (models/waveflow.py:827-852)
 and the known-answer checks that pin the Slaney mel filterbank to librosa's documented output."""
 import numpy as np
+import pytest
 import torch
 
 
@@ -109,3 +110,51 @@ def test_mel_filterbank_known_answers():
         k = np.argmin(np.abs(freqs - c))
         tri = max(0.0, min((freqs[k] - lo) / (c - lo), (hi - freqs[k]) / (hi - c))) * 2.0 / (hi - lo)
         assert abs(fb[i, k] - tri) < 1e-7
+
+
+@pytest.mark.parametrize("channels", [64, 128])
+def test_waveflow_fused_operand_layout(channels):
+    """The packed operands of pk_waveflow_flow / pk_waveflow_layer (include/parakeet_b200.h) restated on the CPU: one
+    ResidualBlock.add_input evaluated as the kernel does it - GEMM1 over [tap][ring slot][channel] | condition columns with the
+    row-step variant's weight, gate per 64-channel block, GEMM2 with the reordered out_proj - against conv2d on the 3-row buffer
+    (reference parakeet/models/waveflow.py:248-285).  Host logic only: no CUDA."""
+    import torch.nn.functional as F
+    from parakeet_b200.models import ConditionalWaveFlow
+    C, M, W = channels, 80, 23
+    m = ConditionalWaveFlow([16, 16], 2, 3, 16, C, M, (3, 3), device="cpu", seed=9)
+    sd = dict(m.state_dict())
+    g = torch.Generator().manual_seed(9)
+    pk = m._pack()
+    nb = C // 64
+    a_rows = torch.cat([torch.cat([torch.arange(64 * k, 64 * k + 64), torch.arange(C + 64 * k, C + 64 * k + 64)]) for k in range(nb)])
+    o_rows = torch.cat([torch.cat([torch.arange(C + 64 * k, C + 64 * k + 64), torch.arange(64 * k, 64 * k + 64)]) for k in range(nb)])
+    from parakeet_b200.models.waveflow import _fold_wn
+    p = {k: v.double() for k, v in _fold_wn({k: v.detach().float() for k, v in sd.items()}).items()}
+    for layer, i in ((0, 1), (1, 5), (2, 15)):                        # width dilation 1, 2, 4; row-step variants 1, 2, 0
+        dil, q = 2 ** layer, f"decoder.1.resnet.{layer}."
+        fused = pk["flows"][1]["layers"][layer]["fused"]
+        rows = {r: torch.randn(C, W, generator=g).double() for r in (i - 3, i - 2, i - 1)}
+        cond = torch.randn(M, W, generator=g).double()
+        # reference: conv2d over the 3-row buffer (causal in height, "same" in width), + condition_proj, gate, out_proj
+        buf = torch.stack([rows[i - 3], rows[i - 2], rows[i - 1]], dim=1)[None]                    # (1, C, 3, W)
+        y = F.conv2d(buf, p[q + "conv.weight"], p[q + "conv.bias"], padding=(0, dil), dilation=(1, dil))[0, :, 0]
+        y = y + p[q + "condition_proj.weight"][:, :, 0, 0] @ cond + p[q + "condition_proj.bias"][:, None]
+        z = torch.tanh(y[:C]) * torch.sigmoid(y[C:])
+        o = p[q + "out_proj.weight"][:, :, 0, 0] @ z + p[q + "out_proj.bias"][:, None]             # res (C) | skip (C)
+        # kernel view: ring slot s holds the row r with r % 3 == s; operand columns [tap][slot][c] then the condition channels
+        w1 = fused["w1"][i % 3].float().sum(0).double()                                            # hi + lo planes
+        w2 = fused["w2"].float().sum(0).double()
+        a_op = torch.zeros(9 * C + 128, W, dtype=torch.float64)
+        for tap in range(3):
+            for s in range(3):
+                r = next(r for r in rows if r % 3 == s)
+                shifted = torch.zeros(C, W, dtype=torch.float64)
+                lo, hi = max(0, -(tap - 1) * dil), min(W, W - (tap - 1) * dil)
+                shifted[:, lo:hi] = rows[r][:, lo + (tap - 1) * dil:hi + (tap - 1) * dil]
+                a_op[(3 * tap + s) * C:(3 * tap + s + 1) * C] = shifted
+        a_op[9 * C:9 * C + M] = cond
+        acc1 = w1 @ a_op + torch.from_numpy(fused["b1"]).double()[:, None]
+        assert torch.allclose(acc1, y[a_rows], rtol=0, atol=2e-4 * y.abs().max().item())           # bf16x2 planes of the weights
+        zk = torch.cat([torch.tanh(acc1[128 * k:128 * k + 64]) * torch.sigmoid(acc1[128 * k + 64:128 * k + 128]) for k in range(nb)])
+        acc2 = w2 @ zk + torch.from_numpy(fused["b2"]).double()[:, None]
+        assert torch.allclose(acc2, o[o_rows], rtol=0, atol=2e-4 * o.abs().max().item())
