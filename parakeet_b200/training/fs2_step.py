@@ -67,6 +67,8 @@ class FastSpeech2TrainStep:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         dev = model.device
         self.dev = dev
+        self.overlap = os.environ.get("PK_TRAIN_OVERLAP", "1") != "0"      # parameter gradients on a side stream (on_side)
+        self._side, self._side_used, self._keep = None, False, []
         names = [k for k in model._params if not k.endswith(BUFFERS)]
         self.buffers = FlatBuffers(model._params, names, dev)      # the model's tensors become views of one flat buffer
         self.flat, self.gflat, self.grads = self.buffers.flat, self.buffers.gflat, self.buffers.grads
@@ -149,13 +151,41 @@ class FastSpeech2TrainStep:
             dys = Split.from_f32(dy8)
         else:
             dys = Split.from_f32(dy)
-        if bname:
-            ops.colsum_(dy.reshape(B * T, cout), self.grads[bname])
+        def param_grads():
+            if bname:
+                ops.colsum_(dy.reshape(B * T, cout), self.grads[bname])
+            self.wgrad(x_saved, dys, wname, kind, cin, cout, taps)
+
+        # the parameter gradients are leaves of the backward graph: they run beside the dx chain (the critical path)
+        self.on_side(param_grads, dy, dys, x_saved)
         dx = None
         if need_dx:
             dx, _ = ops.conv_gemm(dys, self.w_bwd(wname, kind), n=cin, k=cout, taps=taps)
-        self.wgrad(x_saved, dys, wname, kind, cin, cout, taps)
         return dx
+
+    def on_side(self, fn, *keep):
+        """Run fn() on the side stream, after everything issued so far on the current stream (fork); join_side() is the join.
+        The small-batch step is launch / latency bound (~750 kernels of 5-30 us on a few SMs each): the weight-gradient
+        transposes, split-K GEMMs and bias sums overlap the activation-gradient chain - in the captured graph they become
+        parallel branches.  `keep`: tensors fn reads that were allocated on the current stream - held until the join so that the
+        caching allocator (also at capture time) cannot hand their memory to a later tensor while the side branch still reads it."""
+        if not self.overlap:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(cur)
+        self._keep.extend(keep)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._side_used = True
+
+    def join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_used = False
+        self._keep.clear()
 
     def zbuf(self, role, shape):
         """Persistent zero-initialised operand planes (training/wgrad.py: zero_planes): ~250 fill launches per step less."""
@@ -307,21 +337,26 @@ class FastSpeech2TrainStep:
                                   y_batch_stride=T * ld, y_head_stride=dk, y_ld=ld)                               # dK = dS^T Q
             # fused QKV projection: h1 [A] -> [3A]
             dqs = Split.from_f32(dqkv)
-            bsum = torch.zeros(ld, dtype=torch.float32, device=dev)
-            ops.colsum_(dqkv.reshape(B * T, ld), bsum)
-            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
-                self.grads[q + "self_attn." + nm + ".bias"].copy_(bsum[j * A:(j + 1) * A])
             wq_b = self._pack(("b", q + "qkv"), lambda: pack_dev(torch.cat([self.P(q + "self_attn.linear_q.weight"), self.P(q + "self_attn.linear_k.weight"),
                                                                            self.P(q + "self_attn.linear_v.weight")], dim=1).contiguous()))
+
+            def qkv_param_grads(q=q, dqkv=dqkv, dqs=dqs, h1=c["h1"]):
+                bsum = torch.zeros(ld, dtype=torch.float32, device=dev)
+                ops.colsum_(dqkv.reshape(B * T, ld), bsum)
+                for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                    self.grads[q + "self_attn." + nm + ".bias"].copy_(bsum[j * A:(j + 1) * A])
+                Tq, Sq, ksq, KKq = wgrad.plan(B, T, A, ld)
+                xt = self.zbuf(("xt", B, T), (A, KKq))
+                ops.transpose_planes(h1, z=B, rows=T, src_zstride=T * A, ld_src=A, c0=0, cols=A, shift=0, r_out=T, dst=xt, dst_zstride=Tq, ld_dst=KKq)
+                dyt = self.zbuf(("dyt", B, T), (ld, KKq))
+                ops.transpose_planes(dqs, z=B, rows=T, src_zstride=T * ld, ld_src=ld, c0=0, cols=ld, shift=0, r_out=T, dst=dyt, dst_zstride=Tq,
+                                     ld_dst=KKq)
+                gw = wgrad.nt_splitk(xt, dyt, A, ld, Sq, ksq, KKq)
+                for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                    self.grads[q + "self_attn." + nm + ".weight"].copy_(gw[:, j * A:(j + 1) * A])
+
+            self.on_side(qkv_param_grads, dqkv, dqs, c["h1"])
             dh1, _ = ops.conv_gemm(dqs, wq_b, n=A, k=ld)
-            Tq, Sq, ksq, KKq = wgrad.plan(B, T, A, ld)
-            xt = self.zbuf(("xt", B, T), (A, KKq))
-            ops.transpose_planes(c["h1"], z=B, rows=T, src_zstride=T * A, ld_src=A, c0=0, cols=A, shift=0, r_out=T, dst=xt, dst_zstride=Tq, ld_dst=KKq)
-            dyt = self.zbuf(("dyt", B, T), (ld, KKq))
-            ops.transpose_planes(dqs, z=B, rows=T, src_zstride=T * ld, ld_src=ld, c0=0, cols=ld, shift=0, r_out=T, dst=dyt, dst_zstride=Tq, ld_dst=KKq)
-            gw = wgrad.nt_splitk(xt, dyt, A, ld, Sq, ksq, KKq)
-            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
-                self.grads[q + "self_attn." + nm + ".weight"].copy_(gw[:, j * A:(j + 1) * A])
             ops.layer_norm_bwd(c["x0"], self.P(q + "norm1.weight"), dh1, dx, True, self.grads[q + "norm1.weight"], self.grads[q + "norm1.bias"])
         return dx
 
@@ -491,6 +526,7 @@ class FastSpeech2TrainStep:
             self.drop(dx, R["transformer_enc_positional_dropout_rate"], self.site(0, 0, 0), inplace=True)
         _lib.check(L.pk_embed_pe_bwd(_ptr(text), _ptr(dx), m.idim, m.padding_idx, B, T, A, _ptr(self.grads["encoder.embed.0.weight"]),
                                      _ptr(self.grads["encoder.embed.1.alpha"]), st), "pk_embed_pe_bwd")
+        self.join_side()
         return losses
 
     def _forward_backward_graphed(self, batch):
