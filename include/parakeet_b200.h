@@ -440,6 +440,9 @@ int pk_softmax_bwd(const void* p_hi, const void* p_lo, const float* dp, int64_t 
                    void* ds_hi, void* ds_lo, pk_stream_t stream);
 /* out[c] += sum_rows x[row, c] (bias gradients). */
 int pk_colsum(const float* x, int64_t rows, int32_t c, float* out, pk_stream_t stream);
+/* pk_colsum on split planes (rows, ld): out[c] += sum_rows (x_hi + x_lo)[row, c] for c < cols (bias gradients from the split
+ * copy of dY, which - unlike the fp32 dY of a residual stream - nobody updates in place afterwards). */
+int pk_colsum_split(const void* x_hi, const void* x_lo, int64_t rows, int32_t cols, int32_t ld, float* out, pk_stream_t stream);
 /* out[i] = sum_{s < slices} part[s * n + i] (fp32): the reduction of split-K partial products of a weight gradient; overwrites
  * `out` (unlike pk_colsum, which accumulates). */
 int pk_sum_slices(const float* part, int32_t slices, int64_t n, float* out, pk_stream_t stream);

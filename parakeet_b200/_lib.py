@@ -127,6 +127,7 @@ def _declare(L):
         "pk_softmax_bwd": [vp, vp, vp, i64, i32, i32, f32, vp, vp, vp],
         "pk_colsum": [vp, i64, i32, vp, vp],
         "pk_sum_slices": [vp, i32, i64, vp, vp],
+        "pk_colsum_split": [vp, vp, i64, i32, i32, vp, vp],
         "pk_batch_norm_train": [vp, i64, i32, vp, vp, f32, i32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "pk_batch_norm_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, vp],
         "pk_relu_bwd": [vp, vp, i64, vp, vp, vp, vp],

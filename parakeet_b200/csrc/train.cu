@@ -156,6 +156,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   if (ty == 0 && col < c) atomicAdd(out + col, part[0][tx] + part[1][tx] + part[2][tx] + part[3][tx]);
 }
 
+// the same for split planes (rows, ld): out[c] += sum_rows (hi + lo)[row, c], c < cols
+__global__ void __launch_bounds__(256) colsum_split_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                           long long rows, int cols, int ld, float* __restrict__ out) {
+  __shared__ float part[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int col = blockIdx.y * 64 + tx;
+  float s = 0.f;
+  if (col < cols)
+    for (long long r = blockIdx.x * 64LL + ty; r < rows && r < (blockIdx.x + 1) * 64LL; r += 4)
+      s += __bfloat162float(hi[r * ld + col]) + __bfloat162float(lo[r * ld + col]);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < cols) atomicAdd(out + col, part[0][tx] + part[1][tx] + part[2][tx] + part[3][tx]);
+}
+
 // out[i] = sum_s part[s][i]: the reduction of split-K partial products (overwrites: no zero fill, no copy afterwards)
 __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, int s, long long n, float* __restrict__ out,
                                                          int vec) {
@@ -467,6 +482,14 @@ extern "C" int pk_colsum(const float* x, int64_t rows, int32_t c, float* out, pk
   PK_CHECK_ARG(x && out && rows > 0 && c > 0, "bad arguments");
   dim3 grid(static_cast<unsigned>((rows + 63) / 64), (c + 63) / 64);
   colsum_kernel<<<grid, 256, 0, PK_STREAM>>>(x, rows, c, out);
+  PK_LAUNCH_DONE()
+}
+
+extern "C" int pk_colsum_split(const void* x_hi, const void* x_lo, int64_t rows, int32_t cols, int32_t ld, float* out, pk_stream_t stream) {
+  PK_CHECK_ARG(x_hi && x_lo && out && rows > 0 && cols > 0 && ld >= cols, "bad arguments");
+  dim3 grid(static_cast<unsigned>((rows + 63) / 64), (cols + 63) / 64);
+  colsum_split_kernel<<<grid, 256, 0, PK_STREAM>>>(static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), rows, cols,
+                                                   ld, out);
   PK_LAUNCH_DONE()
 }
 

@@ -341,6 +341,13 @@ def colsum_(x, out):
     _lib.check(_lib.lib().pk_colsum(_ptr(x), x.numel() // c, c, _ptr(out), _stream()), "pk_colsum")
 
 
+def colsum_split_(xs, cols, out):
+    """out[c] += sum over all rows of (hi + lo)[..., c], c < cols, for a contiguous Split (..., ld)."""
+    ld = xs.hi.shape[-1]
+    assert xs.hi.is_contiguous() and cols <= ld
+    _lib.check(_lib.lib().pk_colsum_split(_ptr(xs.hi), _ptr(xs.lo), xs.hi.numel() // ld, cols, ld, _ptr(out), _stream()), "pk_colsum_split")
+
+
 def sum_slices(part, out):
     """out = part.sum(0) for fp32 part (S, ...) and contiguous out (split-K reduction; overwrites out)."""
     s = part.shape[0]

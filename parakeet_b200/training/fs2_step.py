@@ -152,12 +152,12 @@ class FastSpeech2TrainStep:
         else:
             dys = Split.from_f32(dy)
         def param_grads():
-            if bname:
-                ops.colsum_(dy.reshape(B * T, cout), self.grads[bname])
+            if bname:      # from the split copy: dy itself may be the residual-stream gradient, which LayerNorm backward updates in place
+                ops.colsum_split_(dys, cout, self.grads[bname])
             self.wgrad(x_saved, dys, wname, kind, cin, cout, taps)
 
         # the parameter gradients are leaves of the backward graph: they run beside the dx chain (the critical path)
-        self.on_side(param_grads, dy, dys, x_saved)
+        self.on_side(param_grads, dys, x_saved)
         dx = None
         if need_dx:
             dx, _ = ops.conv_gemm(dys, self.w_bwd(wname, kind), n=cin, k=cout, taps=taps)
