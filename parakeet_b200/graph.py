@@ -60,6 +60,12 @@ class GraphRunner:
         self.replays += 1
         return out
 
+    def drop(self, key):
+        """Forget one key: its graph (and the memory pool it pins) is released; the key runs eagerly, then is captured again."""
+        self._graphs.pop(key, None)
+        self._seen.discard(key)
+        self._disabled.discard(key)
+
     def clear(self):
         self._graphs.clear()
         self._seen.clear()

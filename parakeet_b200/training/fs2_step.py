@@ -87,6 +87,7 @@ class FastSpeech2TrainStep:
         # backward draws new masks on every replay
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._fb_graphs = GraphRunner(max_graphs=16)
+        self._zp = wgrad.ZeroPlanes(max_geoms=16, on_evict=self._fb_graphs.drop)     # planes and graph of a batch shape go together
         self.use_graphs = (os.environ.get("PK_TRAIN_GRAPH", "1") != "0") if use_graphs is None else bool(use_graphs)
         # workspace of the BatchNorm / LayerNorm reductions: 2 floats per channel (pk_batch_norm_train / _bwd)
         widest = max([model.odim, model.adim] + [int(v.shape[0]) for k, v in model._params.items() if k.startswith("postnet.")])
@@ -188,8 +189,8 @@ class FastSpeech2TrainStep:
         self._keep.clear()
 
     def zbuf(self, role, shape):
-        """Persistent zero-initialised operand planes (training/wgrad.py: zero_planes): ~250 fill launches per step less."""
-        return wgrad.zero_planes(role, shape, self.dev)
+        """Persistent zero-initialised operand planes of the current batch shape (training/wgrad.py: ZeroPlanes)."""
+        return self._zp.get(role, shape, self.dev)
 
     def wgrad(self, x, dys, wname, kind, cin, cout, taps):
         """dW = X^T dY over the flattened (batch, time) axis, split-K (training/wgrad.py)."""
@@ -401,6 +402,7 @@ class FastSpeech2TrainStep:
         st = _stream()
         dev = m.device
         self._packs = {}
+        self._zp.begin(self._batch_key(batch))
         self.gflat.zero_()
         text = batch["text"].to(dev, torch.int64).contiguous()
         B, T = text.shape
@@ -529,12 +531,19 @@ class FastSpeech2TrainStep:
         self.join_side()
         return losses
 
+    _BATCH_ORDER = ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")
+
+    @classmethod
+    def _batch_key(cls, batch):
+        return tuple(tuple(batch[k].shape) for k in cls._BATCH_ORDER)
+
     def _forward_backward_graphed(self, batch):
         dev = self.m.device
-        order = ("text", "text_lengths", "speech", "speech_lengths", "durations", "pitch", "energy")
+        order = self._BATCH_ORDER
         dtypes = (torch.int64, torch.int64, torch.float32, torch.int64, torch.int64, torch.float32, torch.float32)
         tensors = [batch[k].to(dev, dt).contiguous() for k, dt in zip(order, dtypes)]
         key = tuple(tuple(t.shape) for t in tensors)
+        self._zp.touch(key)                      # a replay does not pass through forward_backward: keep the LRU order honest
         fn = lambda *ts: self.forward_backward(dict(zip(order, ts)))
         return self._fb_graphs.run(key, fn, tensors).clone()
 

@@ -165,12 +165,12 @@ def _wgrad_splitk(dys, x, cout, cin, k, shifts):
     dev = dys.hi.device
     cout_p, cin_p = dys.hi.shape[-1], x.hi.shape[-1]
     Tp, S, ks, KKp = wgrad.plan(B, T, cout_p, cin_p)
-    dyt = wgrad.zero_planes(("dyt", B, T), (cout_p, KKp), dev)
+    dyt = wgrad.zero_planes(("dyt", B, T), (cout_p, KKp), dev, geom=("pwg", B, T))
     ops.transpose_planes(dys, z=B, rows=T, src_zstride=T * cout_p, ld_src=cout_p, c0=0, cols=cout_p, shift=0, r_out=T, dst=dyt,
                          dst_zstride=Tp, ld_dst=KKp)
     out = torch.empty(len(shifts), cout_p, cin_p, dtype=torch.float32, device=dev)
     for j, sh in enumerate(shifts):
-        xt = wgrad.zero_planes(("xt", B, T), (cin_p, KKp), dev)
+        xt = wgrad.zero_planes(("xt", B, T), (cin_p, KKp), dev, geom=("pwg", B, T))
         ops.transpose_planes(x, z=B, rows=T, src_zstride=x.hi.stride(0), ld_src=x.hi.stride(1), c0=0, cols=cin_p, shift=sh, r_out=T, dst=xt,
                              dst_zstride=Tp, ld_dst=KKp)
         wgrad.nt_splitk(dyt, xt, cout_p, cin_p, S, ks, KKp, out=out[j])
@@ -216,6 +216,11 @@ class PWGTrainStep:
         import os
         from ..graph import GraphRunner
         self._graphs = GraphRunner(max_graphs=8)
+        # the weight-gradient operand planes (wgrad.zero_planes) are shared per batch geometry and baked into the captured graphs:
+        # if a geometry is evicted (more than 4 distinct batch shapes), every graph of this step is dropped and captured again
+        import weakref
+        ref = weakref.ref(self)
+        wgrad.on_default_evict(lambda geom: ref() is not None and ref()._graphs.clear())
         self.use_graphs = (os.environ.get("PK_TRAIN_GRAPH", "1") != "0") if use_graphs is None else bool(use_graphs)
         if self.world > 1:
             for net in (self.g, self.d):

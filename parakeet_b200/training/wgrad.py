@@ -7,18 +7,70 @@ from .. import ops
 from ..ops import Split
 
 
-_ZERO_PLANES = {}
+class ZeroPlanes:
+    """Persistent zero-initialised split planes for the transposed GEMM operands of the weight gradients.
+
+    `transpose_planes` rewrites the same valid region on every use of a (role, shape) key within one batch geometry and never
+    touches the K padding, so the zeros are written once per geometry instead of by a fill kernel per use (~250 launches per
+    FastSpeech2 step).  Buffers are filed under the current GEOMETRY (`begin(geom)`: the batch shape - it fixes every valid
+    region, and a captured CUDA graph of that batch shape has the buffer addresses baked in).  At most `max_geoms` geometries
+    are kept (LRU): evicting one frees its planes and calls `on_evict(geom)` so that the owner drops the graph captured for it.
+    `role` keeps operands that are alive together apart."""
+
+    def __init__(self, max_geoms=16, on_evict=None):
+        self.max_geoms, self.on_evict = max_geoms, on_evict
+        self._geoms = {}          # geom -> {(role, shape, device): Split}; insertion order = LRU order
+        self._cur = None
+
+    def begin(self, geom):
+        """Make `geom` current (most recently used), evicting the least recently used geometries beyond the bound."""
+        planes = self._geoms.pop(geom, None)
+        self._geoms[geom] = planes if planes is not None else {}
+        self._cur = geom
+        while len(self._geoms) > self.max_geoms:
+            old = next(iter(self._geoms))
+            del self._geoms[old]
+            if self.on_evict is not None:
+                self.on_evict(old)
+
+    touch = begin
+
+    def get(self, role, shape, dev):
+        if self._cur is None:
+            self.begin(None)
+        planes = self._geoms[self._cur]
+        key = (role, tuple(shape), str(dev))
+        buf = planes.get(key)
+        if buf is None:
+            buf = planes[key] = Split.zeros(tuple(shape), dev)
+        return buf
+
+    def __len__(self):
+        return len(self._geoms)
 
 
-def zero_planes(role, shape, dev):
-    """Persistent zero-initialised split planes for a transposed GEMM operand.  `transpose_planes` rewrites the same valid region
-    on every use of a (role, shape) key and never touches the K padding, so the zeros are written once, not by a fill kernel per
-    use.  `role` carries whatever fixes the valid region (batch, time, ...) and keeps operands that are alive together apart."""
-    key = (role, tuple(shape), str(dev))
-    buf = _ZERO_PLANES.get(key)
-    if buf is None:
-        buf = _ZERO_PLANES[key] = Split.zeros(tuple(shape), dev)
-    return buf
+_EVICT_HOOKS = []
+
+
+def _default_evicted(geom):
+    for hook in list(_EVICT_HOOKS):
+        hook(geom)
+
+
+_DEFAULT_PLANES = ZeroPlanes(max_geoms=4, on_evict=_default_evicted)
+
+
+def on_default_evict(hook):
+    """Register hook(geom) for evictions from the module-level cache (a training step that captures CUDA graphs over these planes
+    drops its graphs there: their buffer addresses are baked in)."""
+    _EVICT_HOOKS.append(hook)
+
+
+def zero_planes(role, shape, dev, geom=None):
+    """Module-level cache for callers without their own ZeroPlanes (the PWG training step: fixed batch geometry)."""
+    if geom is not None and geom != _DEFAULT_PLANES._cur:
+        _DEFAULT_PLANES.begin(geom)
+    return _DEFAULT_PLANES.get(role, shape, dev)
 
 
 def plan(batch, t, m, n, max_slices=128):
