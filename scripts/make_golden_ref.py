@@ -244,6 +244,19 @@ def waveflow(out):
         z2 = torch.randn(1, cond2.shape[-1], generator=g)
         out["wf2_mel"], out["wf2_z"] = mel2.numpy(), z2.numpy()
         out["wf2_x"] = ref.decoder.inverse(T(z2), cond2).numpy()
+    # third vector: the SHIPPED config (examples/waveflow/config.py: 128 residual channels), W = 335 columns
+    ref128 = ConditionalWaveFlow(upsample_factors=[16, 16], n_flows=8, n_layers=8, n_group=16, channels=128, n_mels=80, kernel_size=[3, 3])
+    ref128.eval()
+    params128 = owf.synth_params(5, channels=128)
+    check_keys(ref128, params128, "ConditionalWaveFlow(128)")
+    ref128.set_state_dict(params128)
+    g = torch.Generator().manual_seed(45)
+    with torch.no_grad():
+        mel3 = torch.randn(1, 80, 22, generator=g) * 0.5 - 3
+        cond3 = ref128.encoder(T(mel3), trim_conv_artifact=True)
+        z3 = torch.randn(1, cond3.shape[-1], generator=g)
+        out["wf128_mel"], out["wf128_z"] = mel3.numpy(), z3.numpy()
+        out["wf128_x"] = ref128.decoder.inverse(T(z3), cond3).numpy()
 
 
 def wrappers_and_stft(out):

@@ -87,6 +87,12 @@ def test_waveflow_oracle_equals_executed_reference(g):
     with torch.no_grad():
         x2 = owf.infer(folded, mel2, z2)
     assert tuple(x2.shape) == g["wf2_x"].shape and rel_err(x2, torch.from_numpy(g["wf2_x"])) < 1e-5
+    # the shipped config (examples/waveflow/config.py: 128 residual channels), W = 335
+    folded128 = owf.fold_weight_norm(owf.synth_params(5, channels=128))
+    mel3, z3 = torch.from_numpy(g["wf128_mel"]), torch.from_numpy(g["wf128_z"])
+    with torch.no_grad():
+        x3 = owf.infer(folded128, mel3, z3)
+    assert tuple(x3.shape) == g["wf128_x"].shape and rel_err(x3, torch.from_numpy(g["wf128_x"])) < 1e-5
 
 
 def test_inference_wrappers_and_stft_equal_executed_reference(g):
