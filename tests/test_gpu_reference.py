@@ -64,6 +64,12 @@ def test_waveflow_cuda_vs_executed_reference(cuda, g):
     mel2, z2 = torch.from_numpy(g["wf2_mel"]).to(cuda), torch.from_numpy(g["wf2_z"]).to(cuda)
     out2 = wf.infer(mel2, z=z2)
     assert tuple(out2.shape) == g["wf2_x"].shape and rel_err(out2, torch.from_numpy(g["wf2_x"])) < TOL
+    # the reference's shipped config (examples/waveflow/config.py: 128 residual channels), W = 335
+    wf128 = ConditionalWaveFlow([16, 16], 8, 8, 16, 128, 80, (3, 3), device=cuda)
+    wf128.set_state_dict(owf.synth_params(5, channels=128))
+    mel3, z3 = torch.from_numpy(g["wf128_mel"]).to(cuda), torch.from_numpy(g["wf128_z"]).to(cuda)
+    out3 = wf128.infer(mel3, z=z3)
+    assert tuple(out3.shape) == g["wf128_x"].shape and rel_err(out3, torch.from_numpy(g["wf128_x"])) < TOL
 
 
 def test_fs2_multispeaker_tone_cuda_vs_executed_reference(cuda, g):
