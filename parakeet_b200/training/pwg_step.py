@@ -217,7 +217,7 @@ class PWGTrainStep:
         from ..graph import GraphRunner
         self._graphs = GraphRunner(max_graphs=8)
         # the weight-gradient operand planes (wgrad.zero_planes) are shared per batch geometry and baked into the captured graphs:
-        # if a geometry is evicted (more than 4 distinct batch shapes), every graph of this step is dropped and captured again
+        # if a geometry is evicted (more than 16 distinct (batch, length) geometries), every graph of this step is dropped and captured again
         import weakref
         ref = weakref.ref(self)
         wgrad.on_default_evict(lambda geom: ref() is not None and ref()._graphs.clear())

@@ -57,7 +57,7 @@ def _default_evicted(geom):
         hook(geom)
 
 
-_DEFAULT_PLANES = ZeroPlanes(max_geoms=4, on_evict=_default_evicted)
+_DEFAULT_PLANES = ZeroPlanes(max_geoms=16, on_evict=_default_evicted)   # one PWG step uses 2-3 geometries (sample rate, frame rate)
 
 
 def on_default_evict(hook):
